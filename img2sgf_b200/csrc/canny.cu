@@ -1,0 +1,306 @@
+// canny.cu -- Sobel 3x3 + L1 magnitude + non-maximum suppression + hysteresis.
+// Reference call sites: cv.Canny(rgb,50,200,3,L1) img2sgf.py:162-165 (3-channel variant) and the
+// Canny(50,100) that cv.HoughCircles runs on each of its inputs (img2sgf.py:180).
+// Arithmetic: SURVEY.md Appendix A.4 (integer, bit-exact).
+//
+// State map encoding (one byte per pixel): bit0 = NMS candidate (mag > low and local max),
+// bit1 = edge (strong, or weak reached from a strong one).  Final edge <=> bit1.
+#include "canny.cuh"
+#include "profile.cuh"
+
+namespace i2s {
+
+// ------------------------------------------------------------------ Sobel + NMS
+constexpr int NT = 64;                 // output tile (NT x NT), 256 threads
+constexpr int NS_W = NT + 8;           // staged source: x halo 4 (aligned), y halo 2
+constexpr int NS_H = NT + 4;
+constexpr int NM = NT + 2;             // magnitude region (1-px ring around the tile)
+
+template <int CH>
+__global__ void __launch_bounds__(256) k_sobel_nms(const MapSet ms, uint8_t *__restrict__ state,
+                                                   int h, int w, int low, int high, bool al)
+{
+    __shared__ __align__(16) uint8_t s_src[NS_H * NS_W * CH];
+    __shared__ int s_dxy[NM * NM];          // dx | dy << 16 (two's complement halves)
+    __shared__ uint16_t s_mag[NM * NM];
+    const size_t plane = (size_t)h * w;
+    const uint8_t *img = ms.plane(blockIdx.z, plane * CH);
+    const int x0 = blockIdx.x * NT, y0 = blockIdx.y * NT;
+
+    if (CH == 1) {
+        stage_tile_u8(s_src, NS_W, img, h, w, x0 - 4, y0 - 2, NS_W, NS_H, BORDER_REPLICATE, al);
+    } else {
+        for (int idx = threadIdx.x; idx < NS_H * NS_W; idx += blockDim.x) {
+            int ty = idx / NS_W, tx = idx - ty * NS_W;
+            int y = border_index(y0 - 2 + ty, h, BORDER_REPLICATE);
+            int x = border_index(x0 - 4 + tx, w, BORDER_REPLICATE);
+            const uint8_t *p = img + ((size_t)y * w + x) * CH;
+#pragma unroll
+            for (int c = 0; c < CH; c++) s_src[idx * CH + c] = __ldg(p + c);
+        }
+    }
+    __syncthreads();
+
+    // gradients on the (NT+2)^2 ring region; magnitude is 0 outside the image
+    for (int idx = threadIdx.x; idx < NM * NM; idx += blockDim.x) {
+        int ty = idx / NM, tx = idx - ty * NM;
+        int x = x0 - 1 + tx, y = y0 - 1 + ty;
+        int bdx = 0, bdy = 0, bm = 0;
+        if (x >= 0 && x < w && y >= 0 && y < h) {
+            const uint8_t *c = s_src + ((ty + 1) * NS_W + (tx + 3)) * CH;   // centre sample
+            constexpr int RS = NS_W * CH;
+#pragma unroll
+            for (int ch = 0; ch < CH; ch++) {
+                int p00 = c[-RS - CH + ch], p01 = c[-RS + ch], p02 = c[-RS + CH + ch];
+                int p10 = c[-CH + ch], p12 = c[CH + ch];
+                int p20 = c[RS - CH + ch], p21 = c[RS + ch], p22 = c[RS + CH + ch];
+                int dx = (p02 + 2 * p12 + p22) - (p00 + 2 * p10 + p20);
+                int dy = (p20 + 2 * p21 + p22) - (p00 + 2 * p01 + p02);
+                int m = abs(dx) + abs(dy);
+                if (ch == 0 || m > bm) { bm = m; bdx = dx; bdy = dy; }
+            }
+        }
+        s_mag[idx] = (uint16_t)bm;
+        s_dxy[idx] = (int)((uint32_t)(bdx & 0xffff) | ((uint32_t)bdy << 16));
+    }
+    __syncthreads();
+
+    for (int idx = threadIdx.x; idx < NT * (NT / 4); idx += blockDim.x) {
+        int ty = idx / (NT / 4), gx = (idx - ty * (NT / 4)) * 4;
+        int y = y0 + ty, x = x0 + gx;
+        if (y >= h || x >= w) continue;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int c = (ty + 1) * NM + gx + k + 1;
+            int m = s_mag[c];
+            uint32_t st = 0;
+            if (m > low) {
+                int d = s_dxy[c];
+                int xs = (int)(short)(d & 0xffff), ys = d >> 16;
+                int ax = abs(xs), ay = abs(ys) << 15;
+                int t22 = ax * 13573;
+                bool keep;
+                if (ay < t22) keep = m > s_mag[c - 1] && m >= s_mag[c + 1];
+                else {
+                    int t67 = t22 + (ax << 16);
+                    if (ay > t67) keep = m > s_mag[c - NM] && m >= s_mag[c + NM];
+                    else {
+                        int s = (xs ^ ys) < 0 ? -1 : 1;
+                        keep = m > s_mag[c - NM - s] && m > s_mag[c + NM + s];
+                    }
+                }
+                if (keep) st = m > high ? 3u : 1u;
+            }
+            packed |= st << (8 * k);
+        }
+        size_t o = blockIdx.z * plane + (size_t)y * w + x;
+        if (al && x + 3 < w) *reinterpret_cast<uint32_t *>(state + o) = packed;
+        else
+            for (int k = 0; k < 4 && x + k < w; k++) state[o + k] = (uint8_t)(packed >> (8 * k));
+    }
+}
+
+// ------------------------------------------------------------------ hysteresis
+// One block owns a HT x HT tile.  The tile plus a 1-px ring is staged in shared memory;
+// every edge pixel (ring included) seeds a level-synchronous flood over 8-neighbours that
+// promotes candidates INSIDE the tile.  Each pixel enters the queue at most once, so the
+// queue never exceeds the staged area.  A tile whose outermost interior ring changed marks
+// its 8 neighbours dirty for the next pass; passes repeat until no tile is dirty.
+constexpr int HT = 128;
+constexpr int HS_W = HT + 8, HS_H = HT + 2;      // staged: x halo 4 (aligned), y halo 1
+constexpr int HQ = (HT + 2) * (HT + 2);
+
+__global__ void __launch_bounds__(256) k_hysteresis(uint8_t *__restrict__ state, int h, int w, int tiles_x,
+                                                    int tiles_y, uint8_t *dirty_in, uint8_t *dirty_out,
+                                                    int pass, bool al)
+{
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    uint8_t *s_map = s_dyn;                                              // HS_H * HS_W bytes
+    uint16_t *s_q = reinterpret_cast<uint16_t *>(s_dyn + HS_H * HS_W);   // HQ entries
+    __shared__ int s_qn, s_changed, s_ring;
+    const int tile = (blockIdx.z * tiles_y + blockIdx.y) * tiles_x + blockIdx.x;
+    if (pass > 0) {
+        const int d = dirty_in[tile];
+        __syncthreads();                               // everyone has read the flag before it is cleared
+        if (!d) return;
+        if (threadIdx.x == 0) dirty_in[tile] = 0;      // leave the buffer clean for pass+1's writers
+    }
+    const size_t plane = (size_t)h * w;
+    uint8_t *img = state + blockIdx.z * plane;
+    const int x0 = blockIdx.x * HT, y0 = blockIdx.y * HT;
+    if (threadIdx.x == 0) { s_qn = 0; s_changed = 0; s_ring = 0; }
+    stage_tile_u8(s_map, HS_W, img, h, w, x0 - 4, y0 - 1, HS_W, HS_H, BORDER_ZERO, al);
+    __syncthreads();
+    // seeds: every edge pixel of the (HT+2)^2 region; local coords (ly,lx) in [0,HT+1]
+    for (int idx = threadIdx.x; idx < (HT + 2) * (HT + 2); idx += blockDim.x) {
+        int ly = idx / (HT + 2), lx = idx - ly * (HT + 2);
+        if (s_map[ly * HS_W + lx + 3] & 2) s_q[atomicAdd(&s_qn, 1)] = (uint16_t)idx;
+    }
+    int head = 0;
+    while (true) {
+        __syncthreads();
+        int tail = s_qn;
+        __syncthreads();
+        if (head >= tail) break;
+        for (int i = head + threadIdx.x; i < tail; i += blockDim.x) {
+            int p = s_q[i];
+            int ly = p / (HT + 2), lx = p - ly * (HT + 2);
+#pragma unroll
+            for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+                for (int dx = -1; dx <= 1; dx++) {
+                    if (dx == 0 && dy == 0) continue;
+                    int ny = ly + dy, nx = lx + dx;
+                    if (ny < 1 || ny > HT || nx < 1 || nx > HT) continue;   // promote interior only
+                    int b = ny * HS_W + nx + 3;
+                    if ((s_map[b] & 3) != 1) continue;
+                    uint32_t *word = reinterpret_cast<uint32_t *>(s_map + (b & ~3));
+                    int sh = 8 * (b & 3);
+                    uint32_t old = atomicOr(word, 2u << sh);
+                    if (((old >> sh) & 3u) == 1u) {
+                        s_q[atomicAdd(&s_qn, 1)] = (uint16_t)(ny * (HT + 2) + nx);
+                        s_changed = 1;
+                        if (ny == 1 || ny == HT || nx == 1 || nx == HT) s_ring = 1;
+                    }
+                }
+        }
+        head = tail;
+    }
+    if (!s_changed) return;
+    for (int idx = threadIdx.x; idx < HT * (HT / 4); idx += blockDim.x) {
+        int ty = idx / (HT / 4), gx = (idx - ty * (HT / 4)) * 4;
+        int y = y0 + ty, x = x0 + gx;
+        if (y >= h || x >= w) continue;
+        uint32_t v = *reinterpret_cast<const uint32_t *>(s_map + (ty + 1) * HS_W + gx + 4);
+        size_t o = (size_t)y * w + x;
+        if (al && x + 3 < w) *reinterpret_cast<uint32_t *>(img + o) = v;
+        else
+            for (int k = 0; k < 4 && x + k < w; k++) img[o + k] = (uint8_t)(v >> (8 * k));
+    }
+    if (s_ring && threadIdx.x < 9) {
+        int dy = threadIdx.x / 3 - 1, dx = threadIdx.x % 3 - 1;
+        int ty = blockIdx.y + dy, tx = blockIdx.x + dx;
+        if ((dx || dy) && ty >= 0 && ty < tiles_y && tx >= 0 && tx < tiles_x)
+            dirty_out[(blockIdx.z * tiles_y + ty) * tiles_x + tx] = 1;
+    }
+}
+
+// after the last pass: any tile still dirty => that map did not converge
+__global__ void k_hyst_check(const uint8_t *dirty, int tiles_per_map, int n_images, int32_t *status)
+{
+    int map = blockIdx.x;
+    int any = 0;
+    for (int t = threadIdx.x; t < tiles_per_map; t += blockDim.x) any |= dirty[(size_t)map * tiles_per_map + t];
+    any = __syncthreads_or(any);
+    if (any && threadIdx.x == 0) atomicOr(status + map % n_images, I2S_ST_HYST_NOT_CONVERGED);
+}
+
+__global__ void __launch_bounds__(256) k_state_to_edges(const uint8_t *__restrict__ state, uint8_t *__restrict__ edges,
+                                                        size_t total)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        edges[i] = (state[i] & 2) ? 255 : 0;
+}
+
+__global__ void __launch_bounds__(256) k_state_to_edges4(const uint32_t *__restrict__ state, uint32_t *__restrict__ edges,
+                                                         size_t words)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t v = (state[i] >> 1) & 0x01010101u;
+        edges[i] = v * 255u;
+    }
+}
+
+size_t canny_scratch_bytes(int maps, int h, int w)
+{
+    size_t tiles = (size_t)maps * cdiv(w, HT) * cdiv(h, HT);
+    return align_up(tiles, 256) * 2 + 256;
+}
+
+// state: [ms.count * ms.n][h][w], map m = k * ms.n + i belongs to image i (for status)
+int canny_states(const MapSet &ms, int channels, uint8_t *state, int h, int w, int low, int high, int passes,
+                 int32_t *status, void *scratch, cudaStream_t st)
+{
+    const int maps = ms.count * ms.n;
+    bool al = (w & 3) == 0 && ((uintptr_t)state & 3) == 0 && ms.aligned4();
+    dim3 g1(cdiv(w, NT), cdiv(h, NT), maps);
+    {
+    ScopedSection sec(SEC_SOBEL_NMS, st);
+    if (channels == 1) k_sobel_nms<1><<<g1, 256, 0, st>>>(ms, state, h, w, low, high, al);
+    else k_sobel_nms<3><<<g1, 256, 0, st>>>(ms, state, h, w, low, high, al);
+    I2S_CHECK_LAUNCH("k_sobel_nms");
+    }
+    return hysteresis(state, maps, ms.n, h, w, passes, status, scratch, st);
+}
+
+int hysteresis(uint8_t *state, int maps, int n_images, int h, int w, int passes, int32_t *status,
+               void *scratch, cudaStream_t st)
+{
+    bool al = (w & 3) == 0 && ((uintptr_t)state & 3) == 0;
+    ScopedSection sec(SEC_HYSTERESIS, st);
+    int tx = cdiv(w, HT), ty = cdiv(h, HT);
+    size_t tiles = (size_t)maps * tx * ty;
+    uint8_t *d0 = (uint8_t *)scratch, *d1 = d0 + align_up(tiles, 256);
+    I2S_CUDA(cudaMemsetAsync(d0, 0, align_up(tiles, 256) * 2, st));
+    dim3 g(tx, ty, maps);
+    if (passes < 1) passes = 1;
+    constexpr int kSmem = HS_H * HS_W + HQ * 2;
+    static bool attr_done = false;
+    if (!attr_done) {
+        I2S_CUDA(cudaFuncSetAttribute(k_hysteresis, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        attr_done = true;
+    }
+    for (int p = 0; p < passes; p++) {
+        uint8_t *din = (p & 1) ? d1 : d0, *dout = (p & 1) ? d0 : d1;
+        k_hysteresis<<<g, 256, kSmem, st>>>(state, h, w, tx, ty, din, dout, p, al);
+        I2S_CHECK_LAUNCH("k_hysteresis");
+    }
+    uint8_t *last = (passes & 1) ? d1 : d0;   // buffer written by the final pass
+    k_hyst_check<<<maps, 128, 0, st>>>(last, tx * ty, n_images, status);
+    I2S_CHECK_LAUNCH("k_hyst_check");
+    return I2S_OK;
+}
+
+int states_to_edges(const uint8_t *state, uint8_t *edges, size_t total, cudaStream_t st)
+{
+    if (total == 0) return I2S_OK;
+    ScopedSection sec(SEC_STATE_TO_EDGES, st);
+    if (((((uintptr_t)state | (uintptr_t)edges) & 3) == 0) && (total & 3) == 0) {
+        size_t words = total / 4;
+        int blocks = (int)min((size_t)148 * 16, (words + 255) / 256);
+        k_state_to_edges4<<<blocks, 256, 0, st>>>((const uint32_t *)state, (uint32_t *)edges, words);
+    } else {
+        int blocks = (int)min((size_t)148 * 16, (total + 255) / 256);
+        k_state_to_edges<<<blocks, 256, 0, st>>>(state, edges, total);
+    }
+    I2S_CHECK_LAUNCH("k_state_to_edges");
+    return I2S_OK;
+}
+
+}  // namespace i2s
+
+using namespace i2s;
+
+extern "C" size_t i2s_canny_workspace_bytes(int n, int h, int w)
+{
+    if (n <= 0 || h <= 0 || w <= 0) return 256;
+    return canny_scratch_bytes(n, h, w) + 256;
+}
+
+extern "C" int i2s_canny(const uint8_t *img, int channels, uint8_t *edges, int n, int h, int w, int low, int high,
+                         int hyst_passes, int32_t *status, void *ws, size_t ws_bytes, void *stream)
+{
+    I2S_ARG(img && edges && status && ws && n >= 0 && h > 0 && w > 0 && (channels == 1 || channels == 3));
+    if (n == 0) return I2S_OK;
+    if (ws_bytes < i2s_canny_workspace_bytes(n, h, w)) {
+        set_error("i2s_canny: workspace too small (%zu < %zu)", ws_bytes, i2s_canny_workspace_bytes(n, h, w));
+        return I2S_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    // the state map is built in place in `edges` and converted to 0/255 at the end
+    MapSet ms = MapSet::single(img, n);
+    int rc = canny_states(ms, channels, edges, h, w, low, high, hyst_passes, status, ws, st);
+    if (rc) return rc;
+    return states_to_edges(edges, edges, (size_t)n * h * w, st);
+}

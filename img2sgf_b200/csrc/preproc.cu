@@ -1,0 +1,270 @@
+// preproc.cu -- greyscale, PIL contrast, fused Gaussian 3/5/7, median 3/5/7.
+// Reference call sites: img2sgf.py:142-144 (contrast), :153 (grey), :174 (median), :175 (Gaussian).
+// Arithmetic: SURVEY.md Appendix A.1, A.2, A.3, A.9 (all integer / fixed point, bit-exact).
+#include <stdarg.h>
+#include "common.cuh"
+#include "profile.cuh"
+
+namespace i2s {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ------------------------------------------------------------------ grey (A.1)
+__device__ __forceinline__ uint32_t luma_q15(uint32_t c0, uint32_t c1, uint32_t c2)
+{
+    return (3735u * c0 + 19235u * c1 + 9798u * c2 + 16384u) >> 15;
+}
+
+// 4 pixels (12 bytes in, 4 bytes out) per thread; total = n*h*w pixels
+__global__ void __launch_bounds__(256) k_grey4(const uint32_t *__restrict__ rgb, uint32_t *__restrict__ grey,
+                                               size_t quads)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < quads; i += stride) {
+        uint32_t a = __ldg(rgb + 3 * i), b = __ldg(rgb + 3 * i + 1), c = __ldg(rgb + 3 * i + 2);
+        uint32_t p0 = luma_q15(a & 255, (a >> 8) & 255, (a >> 16) & 255);
+        uint32_t p1 = luma_q15(a >> 24, b & 255, (b >> 8) & 255);
+        uint32_t p2 = luma_q15((b >> 16) & 255, b >> 24, c & 255);
+        uint32_t p3 = luma_q15((c >> 8) & 255, (c >> 16) & 255, c >> 24);
+        grey[i] = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_grey1(const uint8_t *__restrict__ rgb, uint8_t *__restrict__ grey,
+                                               size_t first, size_t total)
+{
+    size_t i = first + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride)
+        grey[i] = (uint8_t)luma_q15(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+}
+
+// ------------------------------------------------------------------ contrast (A.9)
+__global__ void __launch_bounds__(256) k_luma_sum(const uint8_t *__restrict__ rgb, unsigned long long *sums,
+                                                  int h, int w)
+{
+    const uint8_t *img = rgb + (size_t)blockIdx.y * h * w * 3;
+    size_t px = (size_t)h * w;
+    unsigned long long s = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < px; i += (size_t)gridDim.x * blockDim.x)
+        s += (19595u * img[3 * i] + 38470u * img[3 * i + 1] + 7471u * img[3 * i + 2] + 0x8000u) >> 16;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(sums + blockIdx.y, s);
+}
+
+__global__ void __launch_bounds__(256) k_contrast(const uint8_t *__restrict__ rgb, uint8_t *__restrict__ out,
+                                                  const unsigned long long *sums, int h, int w, float f)
+{
+    size_t px = (size_t)h * w;
+    int m = (int)((double)sums[blockIdx.y] / (double)px + 0.5);
+    float fm = (float)m;
+    const uint8_t *img = rgb + (size_t)blockIdx.y * px * 3;
+    uint8_t *o = out + (size_t)blockIdx.y * px * 3;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < 3 * px; i += (size_t)gridDim.x * blockDim.x) {
+        float t = __fadd_rn(fm, __fmul_rn(f, __fsub_rn((float)img[i], fm)));
+        o[i] = t <= 0.f ? 0 : (t >= 255.f ? 255 : (uint8_t)t);
+    }
+}
+
+// ------------------------------------------------------------------ Gaussian 3/5/7 fused (A.2)
+// Output tile 128 x 32 per 256-thread block.  Input staged with a halo of 4 (x) / 3 (y),
+// REFLECT_101.  Horizontal pass keeps Q8 sums (<= 65280, u16) for the three kernels in
+// shared memory, vertical pass accumulates Q16 and rounds once.
+constexpr int GT_W = 128, GT_H = 32, GH_X = 4, GH_Y = 3;
+constexpr int GS_W = GT_W + 2 * GH_X;   // 136
+constexpr int GS_H = GT_H + 2 * GH_Y;   // 38
+
+__global__ void __launch_bounds__(256) k_gauss357(const uint8_t *__restrict__ src, uint8_t *__restrict__ d3,
+                                                  uint8_t *__restrict__ d5, uint8_t *__restrict__ d7, int h, int w, bool al)
+{
+    __shared__ __align__(16) uint8_t s_in[GS_H * GS_W];
+    __shared__ __align__(16) uint16_t s_h[3][GS_H][GT_W];
+    const size_t plane = (size_t)h * w;
+    const uint8_t *img = src + blockIdx.z * plane;
+    const int x0 = blockIdx.x * GT_W, y0 = blockIdx.y * GT_H;
+    stage_tile_u8(s_in, GS_W, img, h, w, x0 - GH_X, y0 - GH_Y, GS_W, GS_H, BORDER_REFLECT101, al);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < GS_H * GT_W; idx += blockDim.x) {
+        int ty = idx / GT_W, tx = idx - ty * GT_W;
+        const uint8_t *p = s_in + ty * GS_W + tx + GH_X;
+        int a0 = p[0], a1 = p[-1] + p[1], a2 = p[-2] + p[2], a3 = p[-3] + p[3];
+        s_h[0][ty][tx] = (uint16_t)(88 * a0 + 84 * a1);
+        s_h[1][ty][tx] = (uint16_t)(54 * a0 + 52 * a1 + 49 * a2);
+        s_h[2][ty][tx] = (uint16_t)(38 * a0 + 38 * a1 + 36 * a2 + 35 * a3);
+    }
+    __syncthreads();
+    // each thread: 4 consecutive x of one row, all three kernels
+    for (int idx = threadIdx.x; idx < GT_H * (GT_W / 4); idx += blockDim.x) {
+        int ty = idx / (GT_W / 4), gx = (idx - ty * (GT_W / 4)) * 4;
+        int y = y0 + ty;
+        if (y >= h) continue;
+        uint32_t o3 = 0, o5 = 0, o7 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int tx = gx + k, r = ty + GH_Y;
+            uint32_t v3 = 88u * s_h[0][r][tx] + 84u * (s_h[0][r - 1][tx] + s_h[0][r + 1][tx]);
+            uint32_t v5 = 54u * s_h[1][r][tx] + 52u * (s_h[1][r - 1][tx] + s_h[1][r + 1][tx]) +
+                          49u * (s_h[1][r - 2][tx] + s_h[1][r + 2][tx]);
+            uint32_t v7 = 38u * s_h[2][r][tx] + 38u * (s_h[2][r - 1][tx] + s_h[2][r + 1][tx]) +
+                          36u * (s_h[2][r - 2][tx] + s_h[2][r + 2][tx]) +
+                          35u * (s_h[2][r - 3][tx] + s_h[2][r + 3][tx]);
+            o3 |= min((v3 + 32768u) >> 16, 255u) << (8 * k);
+            o5 |= min((v5 + 32768u) >> 16, 255u) << (8 * k);
+            o7 |= min((v7 + 32768u) >> 16, 255u) << (8 * k);
+        }
+        int x = x0 + gx;
+        size_t o = blockIdx.z * plane + (size_t)y * w + x;
+        if (al && x + 3 < w) {
+            if (d3) *reinterpret_cast<uint32_t *>(d3 + o) = o3;
+            if (d5) *reinterpret_cast<uint32_t *>(d5 + o) = o5;
+            if (d7) *reinterpret_cast<uint32_t *>(d7 + o) = o7;
+        } else {
+            for (int k = 0; k < 4 && x + k < w; k++) {
+                if (d3) d3[o + k] = (uint8_t)(o3 >> (8 * k));
+                if (d5) d5[o + k] = (uint8_t)(o5 >> (8 * k));
+                if (d7) d7[o + k] = (uint8_t)(o7 >> (8 * k));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ median (A.3)
+// Exact b x b median with BORDER_REPLICATE: 8-step radix select on the window held in
+// registers (largest m with #{x < m} <= b*b/2).
+constexpr int MT_W = 64, MT_H = 32;
+
+template <int B> __global__ void __launch_bounds__(256) k_median(const uint8_t *__restrict__ src,
+                                                                 uint8_t *__restrict__ dst, int h, int w, bool al)
+{
+    constexpr int R = B / 2, HX = 4;                 // x halo rounded up to 4 for aligned staging
+    constexpr int SW = MT_W + 2 * HX, SH = MT_H + 2 * R;
+    __shared__ __align__(16) uint8_t s_in[SH * SW];
+    const size_t plane = (size_t)h * w;
+    const uint8_t *img = src + blockIdx.z * plane;
+    uint8_t *out = dst + blockIdx.z * plane;
+    const int x0 = blockIdx.x * MT_W, y0 = blockIdx.y * MT_H;
+    stage_tile_u8(s_in, SW, img, h, w, x0 - HX, y0 - R, SW, SH, BORDER_REPLICATE, al);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < MT_H * (MT_W / 4); idx += blockDim.x) {
+        int ty = idx / (MT_W / 4), gx = (idx - ty * (MT_W / 4)) * 4;
+        int y = y0 + ty, x = x0 + gx;
+        if (y >= h || x >= w) continue;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int v[B * B];
+#pragma unroll
+            for (int dy = 0; dy < B; dy++)
+#pragma unroll
+                for (int dx = 0; dx < B; dx++) v[dy * B + dx] = s_in[(ty + dy) * SW + gx + k + HX - R + dx];
+            int m = 0;
+#pragma unroll
+            for (int bit = 7; bit >= 0; bit--) {
+                int t = m | (1 << bit), c = 0;
+#pragma unroll
+                for (int q = 0; q < B * B; q++) c += (v[q] < t);
+                if (c <= (B * B) / 2) m = t;
+            }
+            packed |= (uint32_t)m << (8 * k);
+        }
+        size_t o = (size_t)y * w + x;
+        if (al && x + 3 < w) *reinterpret_cast<uint32_t *>(out + o) = packed;
+        else
+            for (int k = 0; k < 4 && x + k < w; k++) out[o + k] = (uint8_t)(packed >> (8 * k));
+    }
+}
+
+}  // namespace i2s
+
+using namespace i2s;
+
+extern "C" const char *i2s_last_error(void) { return i2s::g_err; }
+extern "C" int i2s_version(void) { return 100; }
+extern "C" void i2s_default_limits(i2s_limits_t *lim)
+{
+    lim->cand_cap = 8192;
+    lim->circle_cap = 4096;
+    lim->line_cap = 1024;
+    lim->hyst_passes = 8;
+}
+
+extern "C" int i2s_grey(const uint8_t *rgb, uint8_t *grey, int n, int h, int w, void *stream)
+{
+    I2S_ARG(rgb && grey && n >= 0 && h > 0 && w > 0);
+    if (n == 0) return I2S_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t total = (size_t)n * h * w;
+    bool al = ((uintptr_t)rgb & 3) == 0 && ((uintptr_t)grey & 3) == 0;
+    size_t quads = al ? total / 4 : 0;
+    ScopedSection sec(SEC_GREY, st);
+    if (quads) {
+        int blocks = (int)min((size_t)148 * 16, (quads + 255) / 256);
+        k_grey4<<<blocks, 256, 0, st>>>((const uint32_t *)rgb, (uint32_t *)grey, quads);
+        I2S_CHECK_LAUNCH("k_grey4");
+    }
+    if (quads * 4 < total) {
+        size_t rest = total - quads * 4;
+        int blocks = (int)min((size_t)148 * 16, (rest + 255) / 256);
+        k_grey1<<<blocks, 256, 0, st>>>(rgb, grey, quads * 4, total);
+        I2S_CHECK_LAUNCH("k_grey1");
+    }
+    return I2S_OK;
+}
+
+extern "C" int i2s_contrast(const uint8_t *rgb, uint8_t *out, void *scratch8n, int n, int h, int w, double factor,
+                            void *stream)
+{
+    I2S_ARG(rgb && out && scratch8n && n >= 0 && h > 0 && w > 0);
+    if (n == 0) return I2S_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long *sums = (unsigned long long *)scratch8n;
+    I2S_CUDA(cudaMemsetAsync(sums, 0, sizeof(unsigned long long) * n, st));
+    dim3 grid(min(cdiv(h * w, 256 * 8), 148 * 4), n);
+    k_luma_sum<<<grid, 256, 0, st>>>(rgb, sums, h, w);
+    I2S_CHECK_LAUNCH("k_luma_sum");
+    k_contrast<<<grid, 256, 0, st>>>(rgb, out, sums, h, w, (float)factor);
+    I2S_CHECK_LAUNCH("k_contrast");
+    return I2S_OK;
+}
+
+extern "C" int i2s_gauss357(const uint8_t *src, uint8_t *dst3, uint8_t *dst5, uint8_t *dst7, int n, int h, int w,
+                            void *stream)
+{
+    I2S_ARG(src && n >= 0 && h > 0 && w > 0);
+    if (n == 0) return I2S_OK;
+    bool al = (w & 3) == 0 && (((uintptr_t)src | (uintptr_t)dst3 | (uintptr_t)dst5 | (uintptr_t)dst7) & 3) == 0;
+    dim3 grid(cdiv(w, GT_W), cdiv(h, GT_H), n);
+    ScopedSection sec(SEC_GAUSS, (cudaStream_t)stream);
+    k_gauss357<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst3, dst5, dst7, h, w, al);
+    I2S_CHECK_LAUNCH("k_gauss357");
+    return I2S_OK;
+}
+
+extern "C" int i2s_median(const uint8_t *src, uint8_t *dst, int n, int h, int w, int b, void *stream)
+{
+    I2S_ARG(src && dst && n >= 0 && h > 0 && w > 0 && (b == 1 || b == 3 || b == 5 || b == 7));
+    if (n == 0) return I2S_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(cdiv(w, MT_W), cdiv(h, MT_H), n);
+    ScopedSection sec(SEC_MEDIAN, st);
+    bool al = (w & 3) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 3) == 0;
+    if (b == 1) {
+        I2S_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * h * w, cudaMemcpyDeviceToDevice, st));
+    } else if (b == 3) {
+        k_median<3><<<grid, 256, 0, st>>>(src, dst, h, w, al);
+    } else if (b == 5) {
+        k_median<5><<<grid, 256, 0, st>>>(src, dst, h, w, al);
+    } else {
+        k_median<7><<<grid, 256, 0, st>>>(src, dst, h, w, al);
+    }
+    I2S_CHECK_LAUNCH("k_median");
+    return I2S_OK;
+}

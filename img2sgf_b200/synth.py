@@ -5,7 +5,7 @@ spacing `s`, centred; each intersection occupied with probability 0.45, colour u
 {black, white}; black = filled anti-aliased disc, white = white disc with a 2-px black
 anti-aliased outline; optional Gaussian pixel noise; `numpy.random.default_rng(seed)`.
 The drawing is done with a distance-field coverage ramp instead of cv2 drawing calls so the
-bench has no OpenCV dependency; inputs are only ever compared implementation-vs-oracle on the
+bench has no OpenCV dependency; inputs are only ever compared implementation-vs-checker on the
 SAME array, so the exact rasteriser is irrelevant to parity.
 """
 from __future__ import annotations

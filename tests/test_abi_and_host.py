@@ -1,0 +1,136 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/img2sgf_b200.h
+declares (no compute calls), struct layouts match, host logic (sharding, record gather over
+gloo with world_size 2, thresholds, generator) behaves."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    from img2sgf_b200 import build
+    return build.build()
+
+
+def test_header_symbols_exported(built):
+    hdr = open(os.path.join(ROOT, "include", "img2sgf_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(i2s_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 20
+    lib = C.CDLL(built)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    from img2sgf_b200 import _native as N
+    assert sorted(N.EXPORTS) == declared
+    N.lib()     # sets argtypes for all of them
+
+
+def test_struct_layouts(built):
+    from img2sgf_b200 import _native as N
+    assert N.RECORD_DTYPE.itemsize == 384
+    assert N.RECORD_DTYPE.fields["status"][1] == 380
+    assert N.GRID_DTYPE.fields["hcentres"][1] == 32
+    lim = N.default_limits()
+    assert lim.cand_cap >= 1024 and lim.circle_cap >= 1024 and lim.line_cap >= 256 and lim.hyst_passes >= 1
+    assert N.lib().i2s_version() >= 100
+
+
+def test_bad_arguments_fail_loudly(built):
+    """Argument validation happens before any CUDA call, so it can be exercised without a GPU."""
+    from img2sgf_b200 import _native as N
+    rc = N.lib().i2s_grey(None, None, 1, 10, 10, None)
+    assert rc == -1 and b"bad argument" in N.lib().i2s_last_error()
+    with pytest.raises(N.NativeError):
+        N.check(rc, "i2s_grey")
+    lim = N.default_limits()
+    assert N.lib().i2s_pipeline_workspace_bytes(4, 512, 512, C.byref(lim)) > 4 * 512 * 512 * 40
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from img2sgf_b200 import api, _native as N
+    with pytest.raises(N.NativeError):
+        api.edge_map(np.zeros((16, 16, 3), np.uint8))
+    with pytest.raises(N.NativeError):
+        api.process_image(np.zeros((16, 16, 3), np.uint8))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "img2sgf_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.lower(), f
+                assert "import cv2" not in src and "cv2." not in src, f
+
+
+def test_shard_range():
+    from img2sgf_b200.batch import shard_range
+    for total in (0, 1, 7, 8, 17, 8192):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [e - s for s, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_choose_threshold():
+    from img2sgf_b200.api import choose_threshold
+    assert choose_threshold(750, 747) == 74 and choose_threshold(110, 102) == 23
+    assert choose_threshold(10, 10) == 20 and choose_threshold(4000, 4000) == 200
+    assert choose_threshold(2048, 2048) == 176
+
+
+def test_synth_deterministic():
+    from img2sgf_b200 import synth
+    a, ta = synth.diagram(256, 12, 5, seed=7)
+    b, tb = synth.diagram(256, 12, 5, seed=7)
+    assert (a == b).all() and (ta == tb).all() and a.dtype == np.uint8 and set(np.unique(ta)) <= {0, 1, 2}
+    imgs, truths = synth.batch("synth1024", 3, 2)
+    assert imgs.shape == (2, 1024, 1024) and truths.shape == (2, 19, 19)
+
+
+_GLOO_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from img2sgf_b200.batch import shard_range, gather_records, RECORD_BYTES
+rank, world, total = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(sys.argv[2])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+s, e = shard_range(total, rank, world)
+local = torch.zeros((e - s, RECORD_BYTES), dtype=torch.uint8)
+for i in range(s, e):
+    local[i - s] = torch.from_numpy(np.random.default_rng(i).integers(0, 256, RECORD_BYTES, dtype=np.uint8))
+full = gather_records(local, total)
+want = torch.stack([torch.from_numpy(np.random.default_rng(i).integers(0, 256, RECORD_BYTES, dtype=np.uint8))
+                    for i in range(total)]) if total else torch.zeros((0, RECORD_BYTES), dtype=torch.uint8)
+assert full.shape == want.shape and bool((full == want).all()), (rank, full.shape)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+@pytest.mark.parametrize("total", [5, 8])
+def test_gather_records_gloo_world2(tmp_path, total):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    port = 29500 + os.getpid() % 1000 + total
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT, str(total)], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out
+        assert "ok" in out
