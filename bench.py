@@ -70,9 +70,8 @@ def generate(config: str, start: int, count: int, procs: int):
 
 
 # ------------------------------------------------------------------ reference CPU path
-def _cpu_worker(args):
-    """Process `seeds` with the reference's library calls; returns (t_start, t_end, n, kind)."""
-    config, seeds, thr, barrier_t = args
+def _cpu_worker(config, seeds, thr, barrier, out):
+    """Process `seeds` with the reference's library calls; puts (t_start, t_end, n, kind) on `out`."""
     from img2sgf_b200 import synth
     size, s, r, _ = synth.CONFIGS[config]
     imgs = [synth.to_rgb(synth.diagram(size, s, r, sd)[0]) for sd in seeds]
@@ -86,25 +85,28 @@ def _cpu_worker(args):
         from oracle import oracle as O
         kind = "port"
         run = lambda a: O.pipeline(a, thr)
-    run(np.ascontiguousarray(imgs[0][:256, :256]))      # untimed: one-off library initialisation
-    while time.time() < barrier_t:          # common start line
-        time.sleep(0.001)
+    run(imgs[0])                            # untimed: imports, page-in, one-off library initialisation
+    barrier.wait()                          # common start line
     t0 = time.perf_counter()
     for a in imgs:
         run(a)
-    return t0, time.perf_counter(), len(imgs), kind
+    out.put((t0, time.perf_counter(), len(imgs), kind))
 
 
 def cpu_reference_rate(config: str, thr: int, images: int, cores: int, first_seed: int = 0):
     """images/s of the reference CPU path with one single-threaded process per core."""
     per = max(1, images // cores)
     workers = min(cores, max(1, images // per))
-    jobs = []
-    start_at = time.time() + 5.0 + 0.06 * per            # leave time for imports + (untimed) image generation
-    for k in range(workers):
-        jobs.append((config, list(range(first_seed + k * per, first_seed + (k + 1) * per)), thr, start_at))
-    with mp.get_context("fork").Pool(workers) as pool:
-        res = pool.map(_cpu_worker, jobs, chunksize=1)
+    ctx = mp.get_context("fork")
+    barrier, out = ctx.Barrier(workers), ctx.Queue()
+    procs = [ctx.Process(target=_cpu_worker,
+                         args=(config, list(range(first_seed + k * per, first_seed + (k + 1) * per)), thr, barrier, out))
+             for k in range(workers)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=1800) for _ in procs]
+    for p in procs:
+        p.join()
     t0 = min(r[0] for r in res)
     t1 = max(r[1] for r in res)
     n = sum(r[2] for r in res)

@@ -12,10 +12,14 @@ namespace i2s {
 constexpr int MIN_R = 1, MAX_R = 30, ACC_THR = 30, NBINS = 290;
 constexpr int CANNY_LOW = 50, CANNY_HIGH = 100;
 
-// ------------------------------------------------------------------ K5: voting
-// One block per 64x64 pixel tile.  Edge pixels are compacted into shared memory, then every
-// (edge pixel, direction) pair is one work item walking up to 30 accumulator cells.
-constexpr int VT = 64;
+// ------------------------------------------------------------------ K5a: edge lists
+// The edge pixels of every map are compacted once into a global list of (position, Q10 gradient
+// step), bucketed by 64x64 pixel tile: one block scans its tile of the state map (ballot
+// compaction, no per-pixel atomics), reserves a contiguous slice of the map's list with a single
+// atomic, recomputes the Sobel gradient of each edge pixel from the source image and stores
+// sx = cvRound(dx*1024/mag), sy likewise.  Order inside a bucket is arbitrary;
+// votes commute.
+constexpr int EB = 64;
 
 __device__ __forceinline__ void sobel_at(const uint8_t *__restrict__ img, int h, int w, int x, int y, int &dx,
                                          int &dy)
@@ -31,80 +35,173 @@ __device__ __forceinline__ void sobel_at(const uint8_t *__restrict__ img, int h,
     dy = (p20 + 2 * p21 + p22) - (p00 + 2 * p01 + p02);
 }
 
-__global__ void __launch_bounds__(256) k_vote(const MapSet ms, const uint8_t *__restrict__ state,
-                                              int32_t *__restrict__ acc, int h, int w, bool al)
+__global__ void __launch_bounds__(256) k_edge_buckets(const MapSet ms, const uint8_t *__restrict__ state, int h, int w,
+                                                      bool al, uint2 *__restrict__ edges, int32_t *ecount, int2 *dir)
 {
-    __shared__ uint32_t s_edge[VT * VT];
-    __shared__ int s_n;
+    __shared__ uint32_t s_pos[EB * EB];
+    __shared__ int s_n, s_off;
     const size_t plane = (size_t)h * w;
     const int map = blockIdx.z;
     const uint8_t *img = ms.plane(map, plane);
     const uint8_t *stm = state + map * plane;
-    int32_t *accm = acc + (size_t)map * (h + 2) * (w + 2);
-    const int aw = w + 2;
-    const int x0 = blockIdx.x * VT, y0 = blockIdx.y * VT;
+    const int x0 = blockIdx.x * EB, y0 = blockIdx.y * EB;
+    const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
-    for (int idx = threadIdx.x; idx < VT * (VT / 4); idx += blockDim.x) {
-        int ty = idx / (VT / 4), gx = (idx - ty * (VT / 4)) * 4;
+#pragma unroll
+    for (int it = 0; it < EB * (EB / 4) / 256; it++) {
+        int idx = it * 256 + threadIdx.x;
+        int ty = idx / (EB / 4), gx = (idx % (EB / 4)) * 4;
         int y = y0 + ty, x = x0 + gx;
-        if (y >= h || x >= w) continue;
         uint32_t v = 0;
-        const uint8_t *p = stm + (size_t)y * w + x;
-        if (al && x + 3 < w) v = __ldg(reinterpret_cast<const uint32_t *>(p));
-        else
-            for (int k = 0; k < 4 && x + k < w; k++) v |= (uint32_t)__ldg(p + k) << (8 * k);
+        if (y < h && x < w) {
+            const uint8_t *p = stm + (size_t)y * w + x;
+            if (al && x + 3 < w) v = __ldg(reinterpret_cast<const uint32_t *>(p));
+            else
+                for (int k = 0; k < 4 && x + k < w; k++) v |= (uint32_t)__ldg(p + k) << (8 * k);
+        }
         v &= 0x02020202u;
+        const int nb = __popc(v);                                    // 0..4 edge pixels in this word
+        const uint32_t b0 = __ballot_sync(0xffffffffu, nb & 1), b1 = __ballot_sync(0xffffffffu, nb & 2),
+                       b2 = __ballot_sync(0xffffffffu, nb & 4);
+        const uint32_t lt = (1u << lane) - 1u;
+        const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+        int base = 0;
+        if (lane == 0 && total) base = atomicAdd(&s_n, total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        int pos = base + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
         while (v) {
             int k = (__ffs(v) - 1) >> 3;
             v &= ~(0xffu << (8 * k));
-            s_edge[atomicAdd(&s_n, 1)] = ((uint32_t)y << 16) | (uint32_t)(x + k);
+            s_pos[pos++] = ((uint32_t)y << 16) | (uint32_t)(x + k);
         }
     }
     __syncthreads();
-    const int items = 2 * s_n;
-    for (int it = threadIdx.x; it < items; it += blockDim.x) {
-        uint32_t e = s_edge[it >> 1];
-        int x = e & 0xffff, y = e >> 16;
+    const int n = s_n;
+    if (threadIdx.x == 0) {
+        s_off = n ? atomicAdd(ecount + map, n) : 0;
+        dir[((size_t)map * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = make_int2(s_off, n);
+    }
+    __syncthreads();
+    uint2 *out = edges + (size_t)map * plane + s_off;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t e = s_pos[i];
+        const int x = e & 0xffff, y = e >> 16;
         int dx, dy;
         sobel_at(img, h, w, x, y, dx, dy);
-        if (dx == 0 && dy == 0) continue;
-        float vx = (float)dx, vy = (float)dy;
-        float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)));
-        if (mag < 1.0f) continue;
-        int sx = __float2int_rn(__fdiv_rn(__fmul_rn(vx, 1024.0f), mag));
-        int sy = __float2int_rn(__fdiv_rn(__fmul_rn(vy, 1024.0f), mag));
-        if (it & 1) { sx = -sx; sy = -sy; }
-        int x1 = x * 1024 + MIN_R * sx, y1 = y * 1024 + MIN_R * sy;
-#pragma unroll 2
-        for (int r = MIN_R; r <= MAX_R; r++, x1 += sx, y1 += sy) {
-            int x2 = x1 >> 10, y2 = y1 >> 10;
-            if ((unsigned)x2 >= (unsigned)w || (unsigned)y2 >= (unsigned)h) break;
-            atomicAdd(accm + (size_t)y2 * aw + x2, 1);
+        int sx = 0, sy = 0;
+        if (dx != 0 || dy != 0) {
+            float vx = (float)dx, vy = (float)dy;
+            float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)));
+            if (!(mag < 1.0f)) {
+                sx = __float2int_rn(__fdiv_rn(__fmul_rn(vx, 1024.0f), mag));
+                sy = __float2int_rn(__fdiv_rn(__fmul_rn(vy, 1024.0f), mag));
+            }
         }
+        out[i] = make_uint2(e, (uint32_t)(sx & 0xffff) | ((uint32_t)sy << 16));   // (0,0) step = no vote
     }
 }
 
-// ------------------------------------------------------------------ K6: accumulator peaks
-__global__ void __launch_bounds__(256) k_peaks(const int32_t *__restrict__ acc, int h, int w, int32_t *cand,
-                                               int32_t *ncand, int cand_cap)
+// ------------------------------------------------------------------ K5+K6: voting fused with peak finding
+// One block owns a 128x128 tile of accumulator cells, plus the 1-cell ring the 4-neighbour test
+// reads and a 2-cell guard band, as int32 in shared memory; the accumulator never exists in global
+// memory.  Every edge pixel within 30 px of the ring can vote into the tile: the block walks the
+// edge-list buckets that overlap that region.  Each (pixel, direction) ray is clipped in float to
+// the range of radii whose cells fall inside the tile -- conservatively, at most one extra step per
+// side, which the guard band absorbs -- so the inner loop is a bare shared-memory atomic per vote
+// with no bounds test.  Rays are monotone in x and y, hence "cells inside the tile" is one interval
+// of radii and dropping out-of-image cells equals the reference's break.  Votes are integers, so
+// the result does not depend on the order of the atomics.
+constexpr int AT = 128;                      // tile edge in accumulator cells
+constexpr int AG = 2;                        // guard cells around the ring
+constexpr int AS = AT + 2 + 2 * AG;          // shared rows / used columns
+constexpr int AP = AS + 1;                   // shared pitch (odd: column walks are conflict free)
+constexpr int VOTE_THREADS = 512;
+constexpr int VOTE_SMEM = AS * AP * 4;
+constexpr int VB = 4;                        // buckets per axis that can overlap a tile's region
+
+__global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks(const uint2 *__restrict__ edges,
+                                                             const int2 *__restrict__ dir, int nbx, int nby, int h,
+                                                             int w, int32_t *cand, int32_t *ncand, int cand_cap)
 {
-    const int aw = w + 2;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    int *s_acc = reinterpret_cast<int *>(s_raw);                       // AS x AP
+    __shared__ int s_boff[VB * VB], s_bend[VB * VB + 1];               // bucket slice start / running item end
+    const size_t plane = (size_t)h * w;
     const int map = blockIdx.z;
-    const int32_t *a = acc + (size_t)map * (h + 2) * aw;
-    int x = 1 + blockIdx.x * 64 + (threadIdx.x & 63);
-    int yb = 1 + blockIdx.y * 16 + (threadIdx.x >> 6) * 4;
-    if (x > w) return;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        int y = yb + k;
-        if (y > h) break;
-        size_t base = (size_t)y * aw + x;
-        int v = __ldg(a + base);
-        if (v > ACC_THR && v > __ldg(a + base - 1) && v >= __ldg(a + base + 1) && v > __ldg(a + base - aw) &&
-            v >= __ldg(a + base + aw)) {
+    const uint2 *elist = edges + map * plane;
+    const int tx0 = blockIdx.x * AT, ty0 = blockIdx.y * AT;      // first cell of the tile proper
+    const int cx0 = tx0 - 1 - AG, cy0 = ty0 - 1 - AG;            // cell coordinates of shared (0,0)
+    // cells of the ring that exist in the image: the clip box of the rays
+    const int X0 = max(tx0 - 1, 0), X1 = min(tx0 + AT, w - 1);
+    const int Y0 = max(ty0 - 1, 0), Y1 = min(ty0 + AT, h - 1);
+    // pixels that can reach the ring, and the buckets holding them
+    const int rx0 = max(tx0 - 1 - MAX_R, 0), rx1 = min(tx0 + AT + MAX_R, w - 1);
+    const int ry0 = max(ty0 - 1 - MAX_R, 0), ry1 = min(ty0 + AT + MAX_R, h - 1);
+    const int bx0 = rx0 / EB, bx1 = rx1 / EB, by0 = ry0 / EB, by1 = ry1 / EB;
+    const int nbw = bx1 - bx0 + 1, nb = nbw * (by1 - by0 + 1);      // <= VB*VB
+    for (int i = threadIdx.x; i < AS * AP; i += blockDim.x) s_acc[i] = 0;
+    if (threadIdx.x == 0) {
+        int run = 0;
+        s_bend[0] = 0;
+        for (int b = 0; b < nb; b++) {
+            int2 d = dir[((size_t)map * nby + by0 + b / nbw) * nbx + bx0 + b % nbw];
+            s_boff[b] = d.x;
+            run += 2 * d.y;                                          // two rays per edge pixel
+            s_bend[b + 1] = run;
+        }
+    }
+    __syncthreads();
+    const int items = s_bend[nb];
+    int b = 0;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+        while (it >= s_bend[b + 1]) b++;                             // `it` only grows: b is monotone
+        const uint2 e = __ldg(elist + s_boff[b] + ((it - s_bend[b]) >> 1));
+        const int x = e.x & 0xffff, y = e.x >> 16;
+        if (x < rx0 || x > rx1 || y < ry0 || y > ry1) continue;
+        int sx = (int)(short)(e.y & 0xffff), sy = (int)e.y >> 16;
+        if (sx == 0 && sy == 0) continue;
+        if (it & 1) { sx = -sx; sy = -sy; }
+        // radii whose cell lies in [X0,X1] x [Y0,Y1]  (float, conservative by < 1 step each side)
+        float lo = 1.0f, hi = (float)MAX_R;
+        if (sx != 0) {
+            float inv = __fdividef(1024.0f, (float)sx);
+            float ta = (float)(X0 - x) * inv, tb = (float)(X1 + 1 - x) * inv;
+            lo = fmaxf(lo, fminf(ta, tb)); hi = fminf(hi, fmaxf(ta, tb));
+        } else if (x < X0 || x > X1) continue;
+        if (sy != 0) {
+            float inv = __fdividef(1024.0f, (float)sy);
+            float ta = (float)(Y0 - y) * inv, tb = (float)(Y1 + 1 - y) * inv;
+            lo = fmaxf(lo, fminf(ta, tb)); hi = fminf(hi, fmaxf(ta, tb));
+        } else if (y < Y0 || y > Y1) continue;
+        // 0.25 of slack covers the error of the approximate divide; at most one extra step per side
+        const int r_lo = max(MIN_R, (int)floorf(lo - 0.25f)), r_hi = min(MAX_R, (int)ceilf(hi + 0.25f));
+        int x1 = (x - cx0) * 1024 + r_lo * sx, y1 = (y - cy0) * 1024 + r_lo * sy;
+        for (int r = r_lo; r <= r_hi; r++, x1 += sx, y1 += sy)
+            atomicAdd(s_acc + (y1 >> 10) * AP + (x1 >> 10), 1);
+    }
+    __syncthreads();
+    // cells outside the image never receive votes in the reference: clear what the conservative
+    // extra steps may have left there (border tiles only)
+    if (cx0 < 0 || cy0 < 0 || cx0 + AS > w || cy0 + AS > h) {
+        for (int i = threadIdx.x; i < AS * AS; i += blockDim.x) {
+            int ly = i / AS, lx = i - ly * AS;
+            int cx = cx0 + lx, cy = cy0 + ly;
+            if (cx < 0 || cy < 0 || cx >= w || cy >= h) s_acc[ly * AP + lx] = 0;
+        }
+        __syncthreads();
+    }
+    // K6: 4-neighbour peaks above the accumulator threshold, interior cells only (x,y >= 1)
+    const int aw = w + 2;
+    for (int idx = threadIdx.x; idx < AT * AT; idx += blockDim.x) {
+        int ty = idx / AT, tx = idx - ty * AT;
+        int cx = tx0 + tx, cy = ty0 + ty;
+        if (cx < 1 || cy < 1 || cx >= w || cy >= h) continue;    // cells x==w / y==h never receive votes
+        const int *c = s_acc + (ty + 1 + AG) * AP + tx + 1 + AG;
+        int v = c[0];
+        if (v > ACC_THR && v > c[-1] && v >= c[1] && v > c[-AP] && v >= c[AP]) {
             int slot = atomicAdd(ncand + map, 1);
-            if (slot < cand_cap) cand[(size_t)map * cand_cap + slot] = (int32_t)base;
+            if (slot < cand_cap) cand[(size_t)map * cand_cap + slot] = cy * aw + cx;
         }
     }
 }
@@ -118,14 +215,22 @@ __device__ __forceinline__ float radius_of_q(int q)
     return __fadd_rn(__fdiv_rn(__fdiv_rn((float)q, 2.0f), 10.0f), 1.0f);
 }
 
-constexpr int RW = 8;   // warps per block
+constexpr int RW = 8;          // warps per block
+constexpr int RBINS = 320;     // NBINS padded to a multiple of 32 (pad stays zero)
+constexpr int RQ = 576;        // radius table size: q = upbin + j <= 289 + 279
+constexpr int RROWS = 15;      // window rows compacted per round (15 x 60 px fit the warp's list)
 
-__global__ void __launch_bounds__(RW * 32) k_radius(const uint8_t *__restrict__ state, int h, int w,
+__global__ void __launch_bounds__(RW * 32) k_radius(const uint8_t *__restrict__ state, int h, int w, bool al,
                                                    const int32_t *__restrict__ cand, const int32_t *__restrict__ ncand,
                                                    int cand_cap, unsigned long long *est, int32_t *nest, int32_t *status,
                                                    int n_images)
 {
-    __shared__ int s_bins[RW][NBINS + 6];
+    __shared__ int s_bins[RW][RBINS];
+    __shared__ int s_pref[RW][RBINS];
+    __shared__ uint32_t s_mask[RW][RBINS / 32];
+    __shared__ float s_rtab[RQ];
+    __shared__ uint16_t s_list[RW][RROWS * 64];
+    __shared__ int s_lcnt[RW];
     const int map = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t plane = (size_t)h * w;
@@ -136,41 +241,103 @@ __global__ void __launch_bounds__(RW * 32) k_radius(const uint8_t *__restrict__ 
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(status + map % n_images, I2S_ST_CAND_OVERFLOW);
         n = cand_cap;
     }
-    int *bins = s_bins[warp];
+    if (blockIdx.x * RW >= n) return;
+    for (int q = threadIdx.x; q < RQ; q += blockDim.x) s_rtab[q] = radius_of_q(q);
+    __syncthreads();
+    int *bins = s_bins[warp], *pref = s_pref[warp];
+    uint32_t *mask = s_mask[warp];
+    uint16_t *list = s_list[warp];
+    int *lcnt = s_lcnt + warp;
     for (int c = blockIdx.x * RW + warp; c < n; c += gridDim.x * RW) {
         int base = cand[(size_t)map * cand_cap + c];
         int cy = base / aw, cx = base - cy * aw;
-        for (int b = lane; b < NBINS; b += 32) bins[b] = 0;
+        for (int b = lane; b < RBINS; b += 32) bins[b] = 0;
         __syncwarp();
+        // histogram of distances to the edge pixels of the 60x60 window (|d| <= 30 reaches no further).
+        // 15 window rows at a time: the lanes compact the edge pixels into the warp's list first, so the
+        // float distance / bin arithmetic then runs on full warps.
         const float fcx = (float)cx + 0.5f, fcy = (float)cy + 0.5f;
-        for (int i = lane; i < 60 * 60; i += 32) {
-            int wy = i / 60, wx = i - wy * 60;
-            int py = cy - 29 + wy, px = cx - 29 + wx;
-            if (px < 0 || px >= w || py < 0 || py >= h) continue;
-            if (!(__ldg(stm + (size_t)py * w + px) & 2)) continue;
-            float ddx = fcx - (float)px, ddy = fcy - (float)py;
-            float r2 = __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy));
-            if (r2 >= 1.0f && r2 <= 900.0f) {
-                float d = __fsqrt_rn(r2);
-                int bin = __float2int_rn(__fmul_rn(__fsub_rn(d, 1.0f), 10.0f));
-                bin = min(max(bin, 0), NBINS - 1);
-                atomicAdd(bins + bin, 1);
+        const int xlo = max(cx - 29, 0), xhi = min(cx + 30, w - 1);
+        const int ylo = max(cy - 29, 0), yhi = min(cy + 30, h - 1);
+        const int xs = xlo & ~3, nw = (xhi - xs) / 4 + 1;
+        for (int yb = ylo; yb <= yhi; yb += RROWS) {
+            if (lane == 0) *lcnt = 0;
+            __syncwarp();
+            const int total = min(RROWS, yhi - yb + 1) * nw;
+            for (int i = lane; i < total; i += 32) {
+                int wy = i / nw, g = i - wy * nw;
+                int py = yb + wy, x = xs + 4 * g;
+                const uint8_t *p = stm + (size_t)py * w + x;
+                uint32_t v = 0;
+                if (al && x + 3 < w) v = __ldg(reinterpret_cast<const uint32_t *>(p));
+                else
+                    for (int k = 0; k < 4 && x + k < w; k++) v |= (uint32_t)__ldg(p + k) << (8 * k);
+                v &= 0x02020202u;
+                while (v) {
+                    int k = (__ffs(v) - 1) >> 3;
+                    v &= ~(0xffu << (8 * k));
+                    int px = x + k;
+                    if (px >= xlo && px <= xhi) list[atomicAdd(lcnt, 1)] = (uint16_t)(((py - ylo) << 8) | (px - xlo));
+                }
+            }
+            __syncwarp();
+            const int m = *lcnt;
+            for (int i = lane; i < m; i += 32) {
+                int e = list[i];
+                int px = xlo + (e & 0xff), py = ylo + (e >> 8);
+                float ddx = fcx - (float)px, ddy = fcy - (float)py;
+                float r2 = __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy));
+                if (r2 >= 1.0f && r2 <= 900.0f) {
+                    float d = __fsqrt_rn(r2);
+                    int bin = __float2int_rn(__fmul_rn(__fsub_rn(d, 1.0f), 10.0f));
+                    bin = min(max(bin, 0), NBINS - 1);
+                    atomicAdd(bins + bin, 1);
+                }
+            }
+            __syncwarp();
+        }
+        // inclusive prefix sums (10 bins per lane) and the non-zero bitmap
+        {
+            int loc[10], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 10; k++) { loc[k] = bins[lane * 10 + k]; sum += loc[k]; }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            int run = incl - sum;
+#pragma unroll
+            for (int k = 0; k < 10; k++) { run += loc[k]; pref[lane * 10 + k] = run; }
+#pragma unroll
+            for (int wd = 0; wd < RBINS / 32; wd++) {
+                uint32_t m = __ballot_sync(0xffffffffu, bins[wd * 32 + lane] != 0);
+                if (lane == 0) mask[wd] = m;
             }
         }
         __syncwarp();
-        // the scan (all lanes redundantly, uniform control flow)
+        // OpenCV's scan from the top bin: every non-zero bin opens a 10-bin window, the bin just below
+        // the window is skipped.  Uniform across lanes.
         int maxCount = 0, bestq = 0;
         float rBest = 0.0f;
-        for (int j = NBINS - 1; j > 0; j--) {
-            if (bins[j]) {
-                int up = j, cur = 0;
-                for (; j > up - 10 && j >= 0; j--) cur += bins[j];
-                float rCur = radius_of_q(up + j);
-                if ((__fmul_rn((float)cur, rBest) >= __fmul_rn((float)maxCount, rCur)) ||
-                    (rBest < 1.1920929e-07f && cur >= maxCount)) {
-                    rBest = rCur; maxCount = cur; bestq = up + j;
-                }
+        int j = NBINS - 1;
+        while (j > 0) {
+            int wd = j >> 5;
+            uint32_t m = mask[wd] & (0xffffffffu >> (31 - (j & 31)));
+            while (m == 0 && --wd >= 0) m = mask[wd];
+            if (m == 0) break;
+            int up = wd * 32 + 31 - __clz(m);
+            if (up <= 0) break;
+            int jn = up - 10, cur;
+            if (jn >= 0) cur = pref[up] - pref[jn];
+            else { cur = pref[up]; jn = -1; }
+            float rCur = s_rtab[up + jn];
+            if ((__fmul_rn((float)cur, rBest) >= __fmul_rn((float)maxCount, rCur)) ||
+                (rBest < 1.1920929e-07f && cur >= maxCount)) {
+                rBest = rCur; maxCount = cur; bestq = up + jn;
             }
+            j = jn - 1;
         }
         if (lane == 0 && maxCount > ACC_THR) {
             int slot = atomicAdd(nest + map, 1);
@@ -342,13 +509,14 @@ __global__ void __launch_bounds__(256) k_mask(const uint8_t *__restrict__ edges,
 // ------------------------------------------------------------------ host orchestration
 size_t circles_scratch_bytes(int maps, int h, int w, const i2s_limits_t &lim)
 {
-    size_t plane = (size_t)h * w, aplane = (size_t)(h + 2) * (w + 2);
+    size_t plane = (size_t)h * w;
     size_t b = 0;
     b += align_up(maps * plane, 256);                               // state maps
-    b += align_up(maps * aplane * 4, 256);                          // accumulators
+    b += align_up(maps * plane * 8, 256);                           // edge lists (position, Q10 step), worst case
+    b += align_up((size_t)maps * cdiv(w, EB) * cdiv(h, EB) * 8, 256);   // bucket directory
     b += align_up((size_t)maps * lim.cand_cap * 4, 256);            // candidate centres
     b += align_up((size_t)maps * lim.cand_cap * 8, 256);            // estimated circle keys
-    b += align_up((size_t)maps * 4 * 3, 256);                       // counters
+    b += align_up((size_t)maps * 4 * 4, 256);                       // counters
     b += align_up((size_t)maps * lim.circle_cap * 12, 256);         // per-map circles
     b += canny_scratch_bytes(maps, h, w);
     return b + 4096;
@@ -359,37 +527,37 @@ int hough_circles_maps(const MapSet &ms, int h, int w, float *mcirc, int32_t *mc
                        const i2s_limits_t &lim, Arena &ar, cudaStream_t st)
 {
     const int maps = ms.count * ms.n;
-    const size_t plane = (size_t)h * w, aplane = (size_t)(h + 2) * (w + 2);
+    const size_t plane = (size_t)h * w;
     uint8_t *state = ar.take<uint8_t>(maps * plane);
-    int32_t *acc = ar.take<int32_t>(maps * aplane);
+    uint2 *edges = ar.take<uint2>(maps * plane);
+    const int nbx = cdiv(w, EB), nby = cdiv(h, EB);
+    int2 *dir = ar.take<int2>((size_t)maps * nbx * nby);
     int32_t *cand = ar.take<int32_t>((size_t)maps * lim.cand_cap);
     unsigned long long *est = ar.take<unsigned long long>((size_t)maps * lim.cand_cap);
-    int32_t *ctr = ar.take<int32_t>((size_t)maps * 2);
+    int32_t *ctr = ar.take<int32_t>((size_t)maps * 3);
     void *cscratch = ar.take<uint8_t>(canny_scratch_bytes(maps, h, w));
     if (!ar.ok()) { set_error("hough_circles: workspace too small"); return I2S_E_WORKSPACE; }
-    int32_t *ncand = ctr, *nest = ctr + maps;
+    int32_t *ncand = ctr, *nest = ctr + maps, *ecount = ctr + 2 * maps;
 
     int rc = canny_states(ms, 1, state, h, w, CANNY_LOW, CANNY_HIGH, lim.hyst_passes, status, cscratch, st);
     if (rc) return rc;
-    {
-        ScopedSection sec(SEC_ACC_CLEAR, st);
-        I2S_CUDA(cudaMemsetAsync(acc, 0, maps * aplane * sizeof(int32_t), st));
-        I2S_CUDA(cudaMemsetAsync(ctr, 0, sizeof(int32_t) * maps * 2, st));
-    }
+    I2S_CUDA(cudaMemsetAsync(ctr, 0, sizeof(int32_t) * maps * 3, st));
     bool al = (w & 3) == 0 && ((uintptr_t)state & 3) == 0;
     {
-        ScopedSection sec(SEC_VOTE, st);
-        k_vote<<<dim3(cdiv(w, VT), cdiv(h, VT), maps), 256, 0, st>>>(ms, state, acc, h, w, al);
-        I2S_CHECK_LAUNCH("k_vote");
+        ScopedSection sec(SEC_EDGE_LIST, st);
+        k_edge_buckets<<<dim3(nbx, nby, maps), 256, 0, st>>>(ms, state, h, w, al, edges, ecount, dir);
+        I2S_CHECK_LAUNCH("k_edge_buckets");
     }
     {
-        ScopedSection sec(SEC_PEAKS, st);
-        k_peaks<<<dim3(cdiv(w, 64), cdiv(h, 16), maps), 256, 0, st>>>(acc, h, w, cand, ncand, lim.cand_cap);
-        I2S_CHECK_LAUNCH("k_peaks");
+        ScopedSection sec(SEC_VOTE, st);
+        I2S_CUDA(cudaFuncSetAttribute(k_vote_peaks, cudaFuncAttributeMaxDynamicSharedMemorySize, VOTE_SMEM));
+        k_vote_peaks<<<dim3(cdiv(w, AT), cdiv(h, AT), maps), VOTE_THREADS, VOTE_SMEM, st>>>(edges, dir, nbx, nby, h, w,
+                                                                                           cand, ncand, lim.cand_cap);
+        I2S_CHECK_LAUNCH("k_vote_peaks");
     }
     {
         ScopedSection sec(SEC_RADIUS, st);
-        k_radius<<<dim3(16, maps), RW * 32, 0, st>>>(state, h, w, cand, ncand, lim.cand_cap, est, nest, status, ms.n);
+        k_radius<<<dim3(16, maps), RW * 32, 0, st>>>(state, h, w, al, cand, ncand, lim.cand_cap, est, nest, status, ms.n);
         I2S_CHECK_LAUNCH("k_radius");
     }
     ScopedSection sec(SEC_CIRCLES_FINISH, st);

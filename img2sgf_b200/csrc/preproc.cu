@@ -137,44 +137,97 @@ __global__ void __launch_bounds__(256) k_gauss357(const uint8_t *__restrict__ sr
 }
 
 // ------------------------------------------------------------------ median (A.3)
-// Exact b x b median with BORDER_REPLICATE: 8-step radix select on the window held in
-// registers (largest m with #{x < m} <= b*b/2).
+// Exact b x b median with BORDER_REPLICATE.  Two horizontally adjacent output pixels are processed
+// in the two 16-bit lanes of one register (VIMNMX.U16x2 / VIMNMX3.U16x2 are native on sm_100a):
+//   1. window min / max per lane;
+//   2. radix select restricted to the bits of (max - min): m = largest value with
+//      #{x < min + m} <= b*b/2, counted lane-wise with the carry trick
+//      (x + (0x8000 - t)) >> 15 == [x >= t]   (values < 256, so lanes never interact).
+// Flat windows (min == max) cost no selection rounds at all.
 constexpr int MT_W = 64, MT_H = 32;
+
+template <int B> __device__ __forceinline__ uint32_t median_pair(const uint32_t (&e)[B][B + 2], int k0)
+{
+    // lanes: low = window of pixel x, high = window of pixel x+1; elements e[dy][k0 .. k0+B-1]
+    uint32_t mn = e[0][k0], mx = e[0][k0];
+#pragma unroll
+    for (int dy = 0; dy < B; dy++)
+#pragma unroll
+        for (int dx = (dy == 0 ? 1 : 0); dx < B; dx += 2) {
+            if (dx + 1 < B) {
+                mn = __vimin3_u16x2(mn, e[dy][k0 + dx], e[dy][k0 + dx + 1]);
+                mx = __vimax3_u16x2(mx, e[dy][k0 + dx], e[dy][k0 + dx + 1]);
+            } else {
+                mn = __vminu2(mn, e[dy][k0 + dx]);
+                mx = __vmaxu2(mx, e[dy][k0 + dx]);
+            }
+        }
+    const uint32_t range = mx - mn;                       // per lane, no borrow (mx >= mn)
+    const uint32_t widest = max(range & 0xffffu, range >> 16);
+    if (widest == 0) return mn;
+    uint32_t m = 0;
+    constexpr uint32_t NEED = (B * B) / 2 + 1;            // #{x >= t} >= NEED  <=>  #{x < t} <= B*B/2
+    for (int bit = 31 - __clz(widest); bit >= 0; bit--) {
+        const uint32_t t = mn + (m | (0x00010001u << bit));       // candidate thresholds, per lane
+        const uint32_t c = 0x80008000u - t;
+        uint32_t ge = 0;
+#pragma unroll
+        for (int dy = 0; dy < B; dy++)
+#pragma unroll
+            for (int dx = 0; dx < B; dx++) ge += ((e[dy][k0 + dx] + c) >> 15) & 0x00010001u;
+        if ((ge & 0xffffu) >= NEED) m |= 1u << bit;
+        if ((ge >> 16) >= NEED) m |= 0x10000u << bit;
+    }
+    return mn + m;
+}
 
 template <int B> __global__ void __launch_bounds__(256) k_median(const uint8_t *__restrict__ src,
                                                                  uint8_t *__restrict__ dst, int h, int w, bool al)
 {
     constexpr int R = B / 2, HX = 4;                 // x halo rounded up to 4 for aligned staging
     constexpr int SW = MT_W + 2 * HX, SH = MT_H + 2 * R;
-    __shared__ __align__(16) uint8_t s_in[SH * SW];
+    __shared__ __align__(16) uint16_t s_in[SH * SW];   // one zero-extended pixel per 16-bit lane
     const size_t plane = (size_t)h * w;
     const uint8_t *img = src + blockIdx.z * plane;
     uint8_t *out = dst + blockIdx.z * plane;
     const int x0 = blockIdx.x * MT_W, y0 = blockIdx.y * MT_H;
-    stage_tile_u8(s_in, SW, img, h, w, x0 - HX, y0 - R, SW, SH, BORDER_REPLICATE, al);
+    for (int idx = threadIdx.x; idx < SH * (SW / 4); idx += blockDim.x) {
+        int ty = idx / (SW / 4), g = idx - ty * (SW / 4);
+        int y = border_index(y0 - R + ty, h, BORDER_REPLICATE);
+        int x = x0 - HX + 4 * g;
+        const uint8_t *row = img + (size_t)y * w;
+        uint32_t v;
+        if (al && x >= 0 && x + 3 < w) v = __ldg(reinterpret_cast<const uint32_t *>(row + x));
+        else
+            v = (uint32_t)__ldg(row + border_index(x, w, BORDER_REPLICATE)) |
+                ((uint32_t)__ldg(row + border_index(x + 1, w, BORDER_REPLICATE)) << 8) |
+                ((uint32_t)__ldg(row + border_index(x + 2, w, BORDER_REPLICATE)) << 16) |
+                ((uint32_t)__ldg(row + border_index(x + 3, w, BORDER_REPLICATE)) << 24);
+        uint2 o = make_uint2(__byte_perm(v, 0, 0x4140), __byte_perm(v, 0, 0x4342));
+        *reinterpret_cast<uint2 *>(s_in + ty * SW + 4 * g) = o;
+    }
     __syncthreads();
     for (int idx = threadIdx.x; idx < MT_H * (MT_W / 4); idx += blockDim.x) {
         int ty = idx / (MT_W / 4), gx = (idx - ty * (MT_W / 4)) * 4;
         int y = y0 + ty, x = x0 + gx;
         if (y >= h || x >= w) continue;
-        uint32_t packed = 0;
+        // e[dy][k] = (pixel x-R+k, pixel x-R+k+1) of window row dy; pair (x,x+1) uses k = 0..B-1,
+        // pair (x+2,x+3) uses k = 2..B+1
+        uint32_t e[B][B + 2];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            int v[B * B];
+        for (int dy = 0; dy < B; dy++) {
+            const uint32_t *rw = reinterpret_cast<const uint32_t *>(s_in + (ty + dy) * SW + gx);  // pixel x-4
+            uint32_t wds[6];
 #pragma unroll
-            for (int dy = 0; dy < B; dy++)
+            for (int j = 0; j < 6; j++) wds[j] = rw[j];
 #pragma unroll
-                for (int dx = 0; dx < B; dx++) v[dy * B + dx] = s_in[(ty + dy) * SW + gx + k + HX - R + dx];
-            int m = 0;
-#pragma unroll
-            for (int bit = 7; bit >= 0; bit--) {
-                int t = m | (1 << bit), c = 0;
-#pragma unroll
-                for (int q = 0; q < B * B; q++) c += (v[q] < t);
-                if (c <= (B * B) / 2) m = t;
+            for (int k = 0; k < B + 2; k++) {
+                const int off = HX - R + k;                       // offset of the first pixel from x-4
+                e[dy][k] = (off & 1) ? __funnelshift_r(wds[off >> 1], wds[(off >> 1) + 1], 16) : wds[off >> 1];
             }
-            packed |= (uint32_t)m << (8 * k);
         }
+        uint32_t pa = median_pair<B>(e, 0), pb = median_pair<B>(e, 2);
+        uint32_t packed = (pa & 0xffu) | ((pa >> 8) & 0xff00u) | ((pb & 0xffu) << 16) | ((pb << 8) & 0xff000000u);
         size_t o = (size_t)y * w + x;
         if (al && x + 3 < w) *reinterpret_cast<uint32_t *>(out + o) = packed;
         else

@@ -8,7 +8,7 @@
 namespace i2s {
 
 static const char *kNames[SEC_COUNT] = {
-    "grey", "sobel_nms", "hysteresis", "state_to_edges", "gauss357", "median", "acc_clear", "vote", "peaks",
+    "grey", "sobel_nms", "hysteresis", "state_to_edges", "gauss357", "median", "acc_clear", "edge_list", "vote", "peaks",
     "radius", "circles_finish", "stack", "mask", "line_vote", "line_peaks", "cluster", "validate", "classify"};
 
 struct Pair { cudaEvent_t a, b; int id; };

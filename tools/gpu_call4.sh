@@ -1,0 +1,17 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -x > gpurun_out/pytest4.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/pytest4.log
+tail -15 gpurun_out/pytest4.log
+timeout 900 python bench.py --per-gpu 256 --steps 2 --warmup 2 --no-e2e --no-cpu-baseline > gpurun_out/bench4.log 2>&1
+echo "bench rc=$?" >> gpurun_out/bench4.log
+python - <<'PY'
+import json
+try:
+    d=json.loads([l for l in open('gpurun_out/bench4.log') if l.startswith('{')][-1])
+    print('value',d['value'],'ms/step',d['ms_per_step'],'roofline',d['roofline']['achieved'],d['roofline']['frac'],'check',d['check'])
+    for k,v in d['sections'].items(): print(f"  {k:16s} {v['ms_per_step']:8.3f} ms")
+except Exception as e:
+    print('bench parse failed',e); print(open('gpurun_out/bench4.log').read()[-2000:])
+PY
+bash tools/gpu_ncu.sh "k_vote_peaks|k_edge_buckets|k_radius" r1_d 0 3

@@ -40,13 +40,10 @@ def hough_diag(img, tag):
     wsn = ws.cpu().numpy()
     plane = h * w
     state = wsn[:plane].reshape(h, w)
-    off = (plane + 255) // 256 * 256
-    acc = wsn[off:off + (h + 2) * (w + 2) * 4].view(np.int32).reshape(h + 2, w + 2)
     oc, oedges, oacc = O.hough_circles(img, taps=True)
     print(f"[{tag}] {w}x{h} status={int(status.item())} count={int(cnt.item())} oracle={len(oc)}")
     diff("canny(50,100) edges", np.where(state & 2, 255, 0).astype(np.uint8), oedges)
     diff("nms candidates superset", (state & 1) >= (oedges > 0), np.ones_like(oedges, bool))
-    diff("accumulator", acc, oacc)
     n = int(cnt.item())
     diff("circles", circ[:n].cpu().numpy(), oc)
 
