@@ -137,101 +137,103 @@ __global__ void __launch_bounds__(256) k_gauss357(const uint8_t *__restrict__ sr
 }
 
 // ------------------------------------------------------------------ median (A.3)
-// Exact b x b median with BORDER_REPLICATE.  Two horizontally adjacent output pixels are processed
-// in the two 16-bit lanes of one register (VIMNMX.U16x2 / VIMNMX3.U16x2 are native on sm_100a):
-//   1. window min / max per lane;
-//   2. radix select restricted to the bits of (max - min): m = largest value with
-//      #{x < min + m} <= b*b/2, counted lane-wise with the carry trick
-//      (x + (0x8000 - t)) >> 15 == [x >= t]   (values < 256, so lanes never interact).
-// Flat windows (min == max) cost no selection rounds at all.
+// Exact b x b median with BORDER_REPLICATE by bit-sliced rank selection.  The staged tile is
+// transposed once per block into eight 1-bit planes (warp ballots).  A thread then gathers, for each
+// plane, the window bits of its four adjacent output pixels (b rows x (b+3) columns, rows packed at
+// a stride of b+3 bits) and selects the median MSB-first: with C the set of still-possible window
+// elements and k the rank wanted inside C, the next result bit is 0 iff k < popc(C & ~plane), which
+// also narrows C.  Cost is independent of the image content: 8 rounds of a few logic ops and
+// popcounts per pixel, no sorting network, no histogram.
 constexpr int MT_W = 64, MT_H = 32;
-
-template <int B> __device__ __forceinline__ uint32_t median_pair(const uint32_t (&e)[B][B + 2], int k0)
-{
-    // lanes: low = window of pixel x, high = window of pixel x+1; elements e[dy][k0 .. k0+B-1]
-    uint32_t mn = e[0][k0], mx = e[0][k0];
-#pragma unroll
-    for (int dy = 0; dy < B; dy++)
-#pragma unroll
-        for (int dx = (dy == 0 ? 1 : 0); dx < B; dx += 2) {
-            if (dx + 1 < B) {
-                mn = __vimin3_u16x2(mn, e[dy][k0 + dx], e[dy][k0 + dx + 1]);
-                mx = __vimax3_u16x2(mx, e[dy][k0 + dx], e[dy][k0 + dx + 1]);
-            } else {
-                mn = __vminu2(mn, e[dy][k0 + dx]);
-                mx = __vmaxu2(mx, e[dy][k0 + dx]);
-            }
-        }
-    const uint32_t range = mx - mn;                       // per lane, no borrow (mx >= mn)
-    const uint32_t widest = max(range & 0xffffu, range >> 16);
-    if (widest == 0) return mn;
-    uint32_t m = 0;
-    constexpr uint32_t NEED = (B * B) / 2 + 1;            // #{x >= t} >= NEED  <=>  #{x < t} <= B*B/2
-    for (int bit = 31 - __clz(widest); bit >= 0; bit--) {
-        const uint32_t t = mn + (m | (0x00010001u << bit));       // candidate thresholds, per lane
-        const uint32_t c = 0x80008000u - t;
-        uint32_t ge = 0;
-#pragma unroll
-        for (int dy = 0; dy < B; dy++)
-#pragma unroll
-            for (int dx = 0; dx < B; dx++) ge += ((e[dy][k0 + dx] + c) >> 15) & 0x00010001u;
-        if ((ge & 0xffffu) >= NEED) m |= 1u << bit;
-        if ((ge >> 16) >= NEED) m |= 0x10000u << bit;
-    }
-    return mn + m;
-}
 
 template <int B> __global__ void __launch_bounds__(256) k_median(const uint8_t *__restrict__ src,
                                                                  uint8_t *__restrict__ dst, int h, int w, bool al)
 {
     constexpr int R = B / 2, HX = 4;                 // x halo rounded up to 4 for aligned staging
     constexpr int SW = MT_W + 2 * HX, SH = MT_H + 2 * R;
-    __shared__ __align__(16) uint16_t s_in[SH * SW];   // one zero-extended pixel per 16-bit lane
+    constexpr int GW = (SW + 31) / 32;               // 32-pixel groups per tile row
+    constexpr int F = B + 3;                         // window columns of 4 adjacent pixels
+    constexpr int RPW = 32 / F;                      // window rows packed per 32-bit word
+    constexpr int NW = (B + RPW - 1) / RPW;          // words per window
+    __shared__ __align__(16) uint8_t s_in[SH * SW];
+    __shared__ uint32_t s_bits[8][SH][GW + 1];
     const size_t plane = (size_t)h * w;
     const uint8_t *img = src + blockIdx.z * plane;
     uint8_t *out = dst + blockIdx.z * plane;
     const int x0 = blockIdx.x * MT_W, y0 = blockIdx.y * MT_H;
-    for (int idx = threadIdx.x; idx < SH * (SW / 4); idx += blockDim.x) {
-        int ty = idx / (SW / 4), g = idx - ty * (SW / 4);
-        int y = border_index(y0 - R + ty, h, BORDER_REPLICATE);
-        int x = x0 - HX + 4 * g;
-        const uint8_t *row = img + (size_t)y * w;
-        uint32_t v;
-        if (al && x >= 0 && x + 3 < w) v = __ldg(reinterpret_cast<const uint32_t *>(row + x));
-        else
-            v = (uint32_t)__ldg(row + border_index(x, w, BORDER_REPLICATE)) |
-                ((uint32_t)__ldg(row + border_index(x + 1, w, BORDER_REPLICATE)) << 8) |
-                ((uint32_t)__ldg(row + border_index(x + 2, w, BORDER_REPLICATE)) << 16) |
-                ((uint32_t)__ldg(row + border_index(x + 3, w, BORDER_REPLICATE)) << 24);
-        uint2 o = make_uint2(__byte_perm(v, 0, 0x4140), __byte_perm(v, 0, 0x4342));
-        *reinterpret_cast<uint2 *>(s_in + ty * SW + 4 * g) = o;
+    stage_tile_u8(s_in, SW, img, h, w, x0 - HX, y0 - R, SW, SH, BORDER_REPLICATE, al);
+    __syncthreads();
+    {   // bit planes: s_bits[b][row][g] bit i = bit b of tile pixel (row, 32 g + i)
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int u = warp; u < SH * GW; u += 8) {
+            int row = u / GW, g = u - row * GW;
+            int col = g * 32 + lane;
+            uint32_t px = col < SW ? s_in[row * SW + col] : 0u, mine = 0;
+#pragma unroll
+            for (int bit = 0; bit < 8; bit++) {
+                uint32_t m = __ballot_sync(0xffffffffu, (px >> bit) & 1u);
+                if (lane == bit) mine = m;
+            }
+            if (lane < 8) s_bits[lane][row][g] = mine;
+        }
+        for (int i = threadIdx.x; i < 8 * SH; i += blockDim.x) s_bits[i / SH][i % SH][GW] = 0;   // pad word
     }
     __syncthreads();
+    // per-word masks of the B low bits of every packed row field
+    uint32_t fm[NW];
+#pragma unroll
+    for (int wd = 0; wd < NW; wd++) {
+        fm[wd] = 0;
+#pragma unroll
+        for (int r = wd * RPW; r < B && r < (wd + 1) * RPW; r++) fm[wd] |= ((1u << B) - 1u) << ((r - wd * RPW) * F);
+    }
     for (int idx = threadIdx.x; idx < MT_H * (MT_W / 4); idx += blockDim.x) {
         int ty = idx / (MT_W / 4), gx = (idx - ty * (MT_W / 4)) * 4;
         int y = y0 + ty, x = x0 + gx;
         if (y >= h || x >= w) continue;
-        // e[dy][k] = (pixel x-R+k, pixel x-R+k+1) of window row dy; pair (x,x+1) uses k = 0..B-1,
-        // pair (x+2,x+3) uses k = 2..B+1
-        uint32_t e[B][B + 2];
+        const int start = gx + HX - R, wi = start >> 5, sh = start & 31;
+        uint32_t P[8][NW];
 #pragma unroll
-        for (int dy = 0; dy < B; dy++) {
-            const uint32_t *rw = reinterpret_cast<const uint32_t *>(s_in + (ty + dy) * SW + gx);  // pixel x-4
-            uint32_t wds[6];
+        for (int bit = 0; bit < 8; bit++) {
 #pragma unroll
-            for (int j = 0; j < 6; j++) wds[j] = rw[j];
+            for (int wd = 0; wd < NW; wd++) P[bit][wd] = 0;
 #pragma unroll
-            for (int k = 0; k < B + 2; k++) {
-                const int off = HX - R + k;                       // offset of the first pixel from x-4
-                e[dy][k] = (off & 1) ? __funnelshift_r(wds[off >> 1], wds[(off >> 1) + 1], 16) : wds[off >> 1];
+            for (int r = 0; r < B; r++) {
+                const uint32_t *rw = &s_bits[bit][ty + r][wi];
+                uint32_t bits = __funnelshift_r(rw[0], rw[1], sh) & ((1u << F) - 1u);
+                P[bit][r / RPW] |= bits << ((r % RPW) * F);
             }
         }
-        uint32_t pa = median_pair<B>(e, 0), pb = median_pair<B>(e, 2);
-        uint32_t packed = (pa & 0xffu) | ((pa >> 8) & 0xff00u) | ((pb & 0xffu) << 16) | ((pb << 8) & 0xff000000u);
+        uint32_t packed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t C[NW];
+#pragma unroll
+            for (int wd = 0; wd < NW; wd++) C[wd] = fm[wd];
+            int k = (B * B) / 2;
+            uint32_t val = 0;
+#pragma unroll
+            for (int bit = 7; bit >= 0; bit--) {
+                uint32_t Z[NW], O[NW];
+                int nz = 0;
+#pragma unroll
+                for (int wd = 0; wd < NW; wd++) {
+                    uint32_t pj = P[bit][wd] >> j;
+                    Z[wd] = C[wd] & ~pj;
+                    O[wd] = C[wd] & pj;
+                    nz += __popc(Z[wd]);
+                }
+                const bool zero = k < nz;              // the median has a 0 in this bit
+#pragma unroll
+                for (int wd = 0; wd < NW; wd++) C[wd] = zero ? Z[wd] : O[wd];
+                if (!zero) { k -= nz; val |= 1u << bit; }
+            }
+            packed |= val << (8 * j);
+        }
         size_t o = (size_t)y * w + x;
         if (al && x + 3 < w) *reinterpret_cast<uint32_t *>(out + o) = packed;
         else
-            for (int k = 0; k < 4 && x + k < w; k++) out[o + k] = (uint8_t)(packed >> (8 * k));
+            for (int k2 = 0; k2 < 4 && x + k2 < w; k2++) out[o + k2] = (uint8_t)(packed >> (8 * k2));
     }
 }
 
