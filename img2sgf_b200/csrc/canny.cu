@@ -132,10 +132,29 @@ __global__ void __launch_bounds__(256) k_hysteresis(uint8_t *__restrict__ state,
     if (threadIdx.x == 0) { s_qn = 0; s_changed = 0; s_ring = 0; }
     stage_tile_u8(s_map, HS_W, img, h, w, x0 - 4, y0 - 1, HS_W, HS_H, BORDER_ZERO, al);
     __syncthreads();
-    // seeds: every edge pixel of the (HT+2)^2 region; local coords (ly,lx) in [0,HT+1]
-    for (int idx = threadIdx.x; idx < (HT + 2) * (HT + 2); idx += blockDim.x) {
-        int ly = idx / (HT + 2), lx = idx - ly * (HT + 2);
-        if (s_map[ly * HS_W + lx + 3] & 2) s_q[atomicAdd(&s_qn, 1)] = (uint16_t)idx;
+    // seeds: interior candidates that already touch an edge pixel (of the tile or of the ring).  Scanning
+    // from the weak side keeps the queue tiny: most edge pixels have no weak neighbour at all.
+    for (int idx = threadIdx.x; idx < HT * (HT / 4); idx += blockDim.x) {
+        const int ly = idx / (HT / 4) + 1, wx = idx % (HT / 4) + 1;          // staged word wx holds lx = 4wx-3 .. 4wx
+        const uint32_t v = *reinterpret_cast<const uint32_t *>(s_map + ly * HS_W + 4 * wx);
+        uint32_t weak = v & ~(v >> 1) & 0x01010101u;                         // bit0 set, bit1 clear: weak candidate
+        while (weak) {
+            const int k = (__ffs(weak) - 1) >> 3;
+            weak &= ~(1u << (8 * k));
+            const int b = ly * HS_W + 4 * wx + k;
+            const uint8_t *c = s_map + b;
+            const uint32_t nb = c[-HS_W - 1] | c[-HS_W] | c[-HS_W + 1] | c[-1] | c[1] | c[HS_W - 1] | c[HS_W] | c[HS_W + 1];
+            if (!(nb & 2)) continue;
+            uint32_t *word = reinterpret_cast<uint32_t *>(s_map + (b & ~3));
+            const int sh = 8 * (b & 3);
+            const uint32_t old = atomicOr(word, 2u << sh);
+            if (((old >> sh) & 3u) == 1u) {
+                const int lx = 4 * wx + k - 3;
+                s_q[atomicAdd(&s_qn, 1)] = (uint16_t)(ly * (HT + 2) + lx);
+                s_changed = 1;
+                if (ly == 1 || ly == HT || lx == 1 || lx == HT) s_ring = 1;
+            }
+        }
     }
     int head = 0;
     while (true) {

@@ -14,12 +14,12 @@ constexpr int CANNY_LOW = 50, CANNY_HIGH = 100;
 
 // ------------------------------------------------------------------ K5a: edge lists
 // The edge pixels of every map are compacted once into a global list of (position, Q10 gradient
-// step), bucketed by 64x64 pixel tile: one block scans its tile of the state map (ballot
+// step), bucketed by 32x32 pixel tile: one block scans its tile of the state map (ballot
 // compaction, no per-pixel atomics), reserves a contiguous slice of the map's list with a single
 // atomic, recomputes the Sobel gradient of each edge pixel from the source image and stores
 // sx = cvRound(dx*1024/mag), sy likewise.  Order inside a bucket is arbitrary;
 // votes commute.
-constexpr int EB = 64;
+constexpr int EB = 32;
 
 __device__ __forceinline__ void sobel_at(const uint8_t *__restrict__ img, int h, int w, int x, int y, int &dx,
                                          int &dy)
@@ -48,9 +48,9 @@ __global__ void __launch_bounds__(256) k_edge_buckets(const MapSet ms, const uin
     const int lane = threadIdx.x & 31;
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
-#pragma unroll
-    for (int it = 0; it < EB * (EB / 4) / 256; it++) {
-        int idx = it * 256 + threadIdx.x;
+    static_assert(EB * (EB / 4) == 256, "one 32-bit word of the state tile per thread");
+    {
+        int idx = threadIdx.x;
         int ty = idx / (EB / 4), gx = (idx % (EB / 4)) * 4;
         int y = y0 + ty, x = x0 + gx;
         uint32_t v = 0;
@@ -118,7 +118,7 @@ constexpr int AS = AT + 2 + 2 * AG;          // shared rows / used columns
 constexpr int AP = AS + 1;                   // shared pitch (odd: column walks are conflict free)
 constexpr int VOTE_THREADS = 512;
 constexpr int VOTE_SMEM = AS * AP * 4;
-constexpr int VB = 4;                        // buckets per axis that can overlap a tile's region
+constexpr int VB = 7;                        // buckets per axis that can overlap a tile's region
 
 __global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks(const uint2 *__restrict__ edges,
                                                              const int2 *__restrict__ dir, int nbx, int nby, int h,
@@ -141,15 +141,17 @@ __global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks(const uint2 *__rest
     const int bx0 = rx0 / EB, bx1 = rx1 / EB, by0 = ry0 / EB, by1 = ry1 / EB;
     const int nbw = bx1 - bx0 + 1, nb = nbw * (by1 - by0 + 1);      // <= VB*VB
     for (int i = threadIdx.x; i < AS * AP; i += blockDim.x) s_acc[i] = 0;
+    if (threadIdx.x < nb) {
+        int b = threadIdx.x;
+        int2 d = dir[((size_t)map * nby + by0 + b / nbw) * nbx + bx0 + b % nbw];
+        s_boff[b] = d.x;
+        s_bend[b + 1] = 2 * d.y;                                     // two rays per edge pixel
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         int run = 0;
         s_bend[0] = 0;
-        for (int b = 0; b < nb; b++) {
-            int2 d = dir[((size_t)map * nby + by0 + b / nbw) * nbx + bx0 + b % nbw];
-            s_boff[b] = d.x;
-            run += 2 * d.y;                                          // two rays per edge pixel
-            s_bend[b + 1] = run;
-        }
+        for (int b = 0; b < nb; b++) { run += s_bend[b + 1]; s_bend[b + 1] = run; }
     }
     __syncthreads();
     const int items = s_bend[nb];
@@ -218,9 +220,9 @@ __device__ __forceinline__ float radius_of_q(int q)
 constexpr int RW = 8;          // warps per block
 constexpr int RBINS = 320;     // NBINS padded to a multiple of 32 (pad stays zero)
 constexpr int RQ = 576;        // radius table size: q = upbin + j <= 289 + 279
-constexpr int RROWS = 15;      // window rows compacted per round (15 x 60 px fit the warp's list)
 
-__global__ void __launch_bounds__(RW * 32) k_radius(const uint8_t *__restrict__ state, int h, int w, bool al,
+__global__ void __launch_bounds__(RW * 32) k_radius(const uint2 *__restrict__ edges, const int2 *__restrict__ dir,
+                                                   int nbx, int nby, int h, int w,
                                                    const int32_t *__restrict__ cand, const int32_t *__restrict__ ncand,
                                                    int cand_cap, unsigned long long *est, int32_t *nest, int32_t *status,
                                                    int n_images)
@@ -229,12 +231,10 @@ __global__ void __launch_bounds__(RW * 32) k_radius(const uint8_t *__restrict__ 
     __shared__ int s_pref[RW][RBINS];
     __shared__ uint32_t s_mask[RW][RBINS / 32];
     __shared__ float s_rtab[RQ];
-    __shared__ uint16_t s_list[RW][RROWS * 64];
-    __shared__ int s_lcnt[RW];
     const int map = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t plane = (size_t)h * w;
-    const uint8_t *stm = state + map * plane;
+    const uint2 *elist = edges + (size_t)map * h * w;
+    const int2 *mdir = dir + (size_t)map * nbx * nby;
     const int aw = w + 2;
     int n = ncand[map];
     if (n > cand_cap) {
@@ -246,56 +246,34 @@ __global__ void __launch_bounds__(RW * 32) k_radius(const uint8_t *__restrict__ 
     __syncthreads();
     int *bins = s_bins[warp], *pref = s_pref[warp];
     uint32_t *mask = s_mask[warp];
-    uint16_t *list = s_list[warp];
-    int *lcnt = s_lcnt + warp;
     for (int c = blockIdx.x * RW + warp; c < n; c += gridDim.x * RW) {
         int base = cand[(size_t)map * cand_cap + c];
         int cy = base / aw, cx = base - cy * aw;
         for (int b = lane; b < RBINS; b += 32) bins[b] = 0;
         __syncwarp();
-        // histogram of distances to the edge pixels of the 60x60 window (|d| <= 30 reaches no further).
-        // 15 window rows at a time: the lanes compact the edge pixels into the warp's list first, so the
-        // float distance / bin arithmetic then runs on full warps.
+        // histogram of the distances to the edge pixels within 30 px: walk the edge-list buckets
+        // that overlap the 60x60 window (at most 3x3 of them)
         const float fcx = (float)cx + 0.5f, fcy = (float)cy + 0.5f;
         const int xlo = max(cx - 29, 0), xhi = min(cx + 30, w - 1);
         const int ylo = max(cy - 29, 0), yhi = min(cy + 30, h - 1);
-        const int xs = xlo & ~3, nw = (xhi - xs) / 4 + 1;
-        for (int yb = ylo; yb <= yhi; yb += RROWS) {
-            if (lane == 0) *lcnt = 0;
-            __syncwarp();
-            const int total = min(RROWS, yhi - yb + 1) * nw;
-            for (int i = lane; i < total; i += 32) {
-                int wy = i / nw, g = i - wy * nw;
-                int py = yb + wy, x = xs + 4 * g;
-                const uint8_t *p = stm + (size_t)py * w + x;
-                uint32_t v = 0;
-                if (al && x + 3 < w) v = __ldg(reinterpret_cast<const uint32_t *>(p));
-                else
-                    for (int k = 0; k < 4 && x + k < w; k++) v |= (uint32_t)__ldg(p + k) << (8 * k);
-                v &= 0x02020202u;
-                while (v) {
-                    int k = (__ffs(v) - 1) >> 3;
-                    v &= ~(0xffu << (8 * k));
-                    int px = x + k;
-                    if (px >= xlo && px <= xhi) list[atomicAdd(lcnt, 1)] = (uint16_t)(((py - ylo) << 8) | (px - xlo));
+        for (int by = ylo / EB; by <= yhi / EB; by++)
+            for (int bx = xlo / EB; bx <= xhi / EB; bx++) {
+                const int2 d = __ldg(mdir + by * nbx + bx);
+                for (int i = lane; i < d.y; i += 32) {
+                    const uint32_t e = __ldg(&elist[d.x + i].x);
+                    const int px = e & 0xffff, py = e >> 16;
+                    if (px < xlo || px > xhi || py < ylo || py > yhi) continue;
+                    float ddx = fcx - (float)px, ddy = fcy - (float)py;
+                    float r2 = __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy));
+                    if (r2 >= 1.0f && r2 <= 900.0f) {
+                        float dd = __fsqrt_rn(r2);
+                        int bin = __float2int_rn(__fmul_rn(__fsub_rn(dd, 1.0f), 10.0f));
+                        bin = min(max(bin, 0), NBINS - 1);
+                        atomicAdd(bins + bin, 1);
+                    }
                 }
             }
-            __syncwarp();
-            const int m = *lcnt;
-            for (int i = lane; i < m; i += 32) {
-                int e = list[i];
-                int px = xlo + (e & 0xff), py = ylo + (e >> 8);
-                float ddx = fcx - (float)px, ddy = fcy - (float)py;
-                float r2 = __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy));
-                if (r2 >= 1.0f && r2 <= 900.0f) {
-                    float d = __fsqrt_rn(r2);
-                    int bin = __float2int_rn(__fmul_rn(__fsub_rn(d, 1.0f), 10.0f));
-                    bin = min(max(bin, 0), NBINS - 1);
-                    atomicAdd(bins + bin, 1);
-                }
-            }
-            __syncwarp();
-        }
+        __syncwarp();
         // inclusive prefix sums (10 bins per lane) and the non-zero bitmap
         {
             int loc[10], sum = 0;
@@ -557,7 +535,7 @@ int hough_circles_maps(const MapSet &ms, int h, int w, float *mcirc, int32_t *mc
     }
     {
         ScopedSection sec(SEC_RADIUS, st);
-        k_radius<<<dim3(16, maps), RW * 32, 0, st>>>(state, h, w, al, cand, ncand, lim.cand_cap, est, nest, status, ms.n);
+        k_radius<<<dim3(16, maps), RW * 32, 0, st>>>(edges, dir, nbx, nby, h, w, cand, ncand, lim.cand_cap, est, nest, status, ms.n);
         I2S_CHECK_LAUNCH("k_radius");
     }
     ScopedSection sec(SEC_CIRCLES_FINISH, st);
