@@ -14,15 +14,16 @@ namespace i2s {
 constexpr int NT = 64;                 // output tile (NT x NT), 256 threads
 constexpr int NS_W = NT + 8;           // staged source: x halo 4 (aligned), y halo 2
 constexpr int NS_H = NT + 4;
-constexpr int NM = NT + 2;             // magnitude region (1-px ring around the tile)
+constexpr int NM = NT + 2;             // magnitude rows (tile + 1-px ring)
+constexpr int NMP = NS_W;              // magnitude row pitch = staged pitch (column index = staged column)
 
 template <int CH>
 __global__ void __launch_bounds__(256) k_sobel_nms(const MapSet ms, uint8_t *__restrict__ state,
                                                    int h, int w, int low, int high, bool al)
 {
     __shared__ __align__(16) uint8_t s_src[NS_H * NS_W * CH];
-    __shared__ int s_dxy[NM * NM];          // dx | dy << 16 (two's complement halves)
-    __shared__ uint16_t s_mag[NM * NM];
+    __shared__ __align__(16) int s_dxy[NM * NMP];          // dx | dy << 16 (two's complement halves)
+    __shared__ __align__(16) uint16_t s_mag[NM * NMP];
     const size_t plane = (size_t)h * w;
     const uint8_t *img = ms.plane(blockIdx.z, plane * CH);
     const int x0 = blockIdx.x * NT, y0 = blockIdx.y * NT;
@@ -41,27 +42,68 @@ __global__ void __launch_bounds__(256) k_sobel_nms(const MapSet ms, uint8_t *__r
     }
     __syncthreads();
 
-    // gradients on the (NT+2)^2 ring region; magnitude is 0 outside the image
-    for (int idx = threadIdx.x; idx < NM * NM; idx += blockDim.x) {
-        int ty = idx / NM, tx = idx - ty * NM;
-        int x = x0 - 1 + tx, y = y0 - 1 + ty;
-        int bdx = 0, bdy = 0, bm = 0;
-        if (x >= 0 && x < w && y >= 0 && y < h) {
-            const uint8_t *c = s_src + ((ty + 1) * NS_W + (tx + 3)) * CH;   // centre sample
-            constexpr int RS = NS_W * CH;
+    // gradients for rows y0-1 .. y0+NT (the tile and its 1-px ring) at every staged column;
+    // magnitude is 0 outside the image.  Array index = mr * NMP + staged column.
+    if (CH == 1) {
+        // four pixels per thread from three staged rows: column sums v = t + 2m + b and column
+        // differences d = b - t give dx_i = v_{i+1} - v_{i-1}, dy_i = d_{i-1} + 2 d_i + d_{i+1}
+        constexpr int G = NS_W / 4;
+        for (int idx = threadIdx.x; idx < NM * G; idx += blockDim.x) {
+            const int mr = idx / G, g = idx - mr * G;
+            const int y = y0 - 1 + mr;
+            const uint32_t *r0 = reinterpret_cast<const uint32_t *>(s_src + mr * NS_W);
+            const uint32_t *r1 = r0 + G, *r2 = r1 + G;
+            const int ga = g > 0 ? g - 1 : 0, gc = g < G - 1 ? g + 1 : G - 1;   // clamped: only unused columns see it
+            int v[6], d[6];
+            {
+                const uint32_t ta = r0[ga], tb = r0[g], tc = r0[gc];
+                const uint32_t ma = r1[ga], mb = r1[g], mc = r1[gc];
+                const uint32_t ba = r2[ga], bb = r2[g], bc = r2[gc];
+                int t, m, b;
+                t = ta >> 24; m = ma >> 24; b = ba >> 24; v[0] = t + 2 * m + b; d[0] = b - t;
 #pragma unroll
-            for (int ch = 0; ch < CH; ch++) {
-                int p00 = c[-RS - CH + ch], p01 = c[-RS + ch], p02 = c[-RS + CH + ch];
-                int p10 = c[-CH + ch], p12 = c[CH + ch];
-                int p20 = c[RS - CH + ch], p21 = c[RS + ch], p22 = c[RS + CH + ch];
-                int dx = (p02 + 2 * p12 + p22) - (p00 + 2 * p10 + p20);
-                int dy = (p20 + 2 * p21 + p22) - (p00 + 2 * p01 + p02);
-                int m = abs(dx) + abs(dy);
-                if (ch == 0 || m > bm) { bm = m; bdx = dx; bdy = dy; }
+                for (int k = 0; k < 4; k++) {
+                    t = (tb >> (8 * k)) & 0xff; m = (mb >> (8 * k)) & 0xff; b = (bb >> (8 * k)) & 0xff;
+                    v[k + 1] = t + 2 * m + b; d[k + 1] = b - t;
+                }
+                t = tc & 0xff; m = mc & 0xff; b = bc & 0xff; v[5] = t + 2 * m + b; d[5] = b - t;
             }
+            int4 oxy;
+            uint32_t om[2] = {0, 0};
+            int *po = &oxy.x;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int dx = v[i + 2] - v[i], dy = d[i] + 2 * d[i + 1] + d[i + 2];
+                const int x = x0 - 4 + 4 * g + i;
+                const int mg = (x >= 0 && x < w && y >= 0 && y < h) ? abs(dx) + abs(dy) : 0;
+                po[i] = (int)((uint32_t)(dx & 0xffff) | ((uint32_t)dy << 16));
+                om[i >> 1] |= (uint32_t)mg << (16 * (i & 1));
+            }
+            *reinterpret_cast<int4 *>(s_dxy + mr * NMP + 4 * g) = oxy;
+            *reinterpret_cast<uint2 *>(s_mag + mr * NMP + 4 * g) = make_uint2(om[0], om[1]);
         }
-        s_mag[idx] = (uint16_t)bm;
-        s_dxy[idx] = (int)((uint32_t)(bdx & 0xffff) | ((uint32_t)bdy << 16));
+    } else {
+        for (int idx = threadIdx.x; idx < NM * NMP; idx += blockDim.x) {
+            const int mr = idx / NMP, col = idx - mr * NMP;
+            const int x = x0 - 4 + col, y = y0 - 1 + mr;
+            int bdx = 0, bdy = 0, bm = 0;
+            if (col >= 1 && col < NS_W - 1 && x >= 0 && x < w && y >= 0 && y < h) {
+                const uint8_t *c = s_src + ((mr + 1) * NS_W + col) * CH;   // centre sample
+                constexpr int RS = NS_W * CH;
+#pragma unroll
+                for (int ch = 0; ch < CH; ch++) {
+                    int p00 = c[-RS - CH + ch], p01 = c[-RS + ch], p02 = c[-RS + CH + ch];
+                    int p10 = c[-CH + ch], p12 = c[CH + ch];
+                    int p20 = c[RS - CH + ch], p21 = c[RS + ch], p22 = c[RS + CH + ch];
+                    int dx = (p02 + 2 * p12 + p22) - (p00 + 2 * p10 + p20);
+                    int dy = (p20 + 2 * p21 + p22) - (p00 + 2 * p01 + p02);
+                    int m = abs(dx) + abs(dy);
+                    if (ch == 0 || m > bm) { bm = m; bdx = dx; bdy = dy; }
+                }
+            }
+            s_mag[idx] = (uint16_t)bm;
+            s_dxy[idx] = (int)((uint32_t)(bdx & 0xffff) | ((uint32_t)bdy << 16));
+        }
     }
     __syncthreads();
 
@@ -72,7 +114,7 @@ __global__ void __launch_bounds__(256) k_sobel_nms(const MapSet ms, uint8_t *__r
         uint32_t packed = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const int c = (ty + 1) * NM + gx + k + 1;
+            const int c = (ty + 1) * NMP + gx + k + 4;
             int m = s_mag[c];
             uint32_t st = 0;
             if (m > low) {
@@ -84,10 +126,10 @@ __global__ void __launch_bounds__(256) k_sobel_nms(const MapSet ms, uint8_t *__r
                 if (ay < t22) keep = m > s_mag[c - 1] && m >= s_mag[c + 1];
                 else {
                     int t67 = t22 + (ax << 16);
-                    if (ay > t67) keep = m > s_mag[c - NM] && m >= s_mag[c + NM];
+                    if (ay > t67) keep = m > s_mag[c - NMP] && m >= s_mag[c + NMP];
                     else {
                         int s = (xs ^ ys) < 0 ? -1 : 1;
-                        keep = m > s_mag[c - NM - s] && m > s_mag[c + NM + s];
+                        keep = m > s_mag[c - NMP - s] && m > s_mag[c + NMP + s];
                     }
                 }
                 if (keep) st = m > high ? 3u : 1u;

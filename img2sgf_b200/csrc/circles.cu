@@ -36,23 +36,26 @@ __device__ __forceinline__ void sobel_at(const uint8_t *__restrict__ img, int h,
 }
 
 __global__ void __launch_bounds__(256) k_edge_buckets(const MapSet ms, const uint8_t *__restrict__ state, int h, int w,
-                                                      bool al, uint2 *__restrict__ edges, int32_t *ecount, int2 *dir)
+                                                      bool al, uint2 *__restrict__ edges, int32_t *ecount, int2 *dir,
+                                                      int nbx, int nby)
 {
-    __shared__ uint32_t s_pos[EB * EB];
-    __shared__ int s_n, s_off;
+    // one block compacts a 2x2 group of buckets (64x64 pixels)
+    __shared__ uint32_t s_pos[4][EB * EB];
+    __shared__ int s_n[4], s_off[4], s_end[5];
+    static_assert(EB * (EB / 4) == 256, "one 32-bit word of a bucket's state tile per thread");
     const size_t plane = (size_t)h * w;
     const int map = blockIdx.z;
     const uint8_t *img = ms.plane(map, plane);
     const uint8_t *stm = state + map * plane;
-    const int x0 = blockIdx.x * EB, y0 = blockIdx.y * EB;
     const int lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) s_n = 0;
+    if (threadIdx.x < 4) s_n[threadIdx.x] = 0;
     __syncthreads();
-    static_assert(EB * (EB / 4) == 256, "one 32-bit word of the state tile per thread");
-    {
-        int idx = threadIdx.x;
-        int ty = idx / (EB / 4), gx = (idx % (EB / 4)) * 4;
-        int y = y0 + ty, x = x0 + gx;
+#pragma unroll
+    for (int sub = 0; sub < 4; sub++) {
+        const int bxx = blockIdx.x * 2 + (sub & 1), byy = blockIdx.y * 2 + (sub >> 1);
+        if (bxx >= nbx || byy >= nby) continue;                      // block-uniform
+        const int ty = threadIdx.x / (EB / 4), gx = (threadIdx.x % (EB / 4)) * 4;
+        const int y = byy * EB + ty, x = bxx * EB + gx;
         uint32_t v = 0;
         if (y < h && x < w) {
             const uint8_t *p = stm + (size_t)y * w + x;
@@ -67,25 +70,40 @@ __global__ void __launch_bounds__(256) k_edge_buckets(const MapSet ms, const uin
         const uint32_t lt = (1u << lane) - 1u;
         const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
         int base = 0;
-        if (lane == 0 && total) base = atomicAdd(&s_n, total);
+        if (lane == 0 && total) base = atomicAdd(&s_n[sub], total);
         base = __shfl_sync(0xffffffffu, base, 0);
         int pos = base + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
         while (v) {
             int k = (__ffs(v) - 1) >> 3;
             v &= ~(0xffu << (8 * k));
-            s_pos[pos++] = ((uint32_t)y << 16) | (uint32_t)(x + k);
+            s_pos[sub][pos++] = ((uint32_t)y << 16) | (uint32_t)(x + k);
         }
     }
     __syncthreads();
-    const int n = s_n;
-    if (threadIdx.x == 0) {
-        s_off = n ? atomicAdd(ecount + map, n) : 0;
-        dir[((size_t)map * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = make_int2(s_off, n);
+    if (threadIdx.x < 4) {
+        const int sub = threadIdx.x;
+        const int bxx = blockIdx.x * 2 + (sub & 1), byy = blockIdx.y * 2 + (sub >> 1);
+        const int n = s_n[sub];
+        int off = 0;
+        if (bxx < nbx && byy < nby) {
+            off = n ? atomicAdd(ecount + map, n) : 0;
+            dir[((size_t)map * nby + byy) * nbx + bxx] = make_int2(off, n);
+        }
+        s_off[sub] = off;
     }
     __syncthreads();
-    uint2 *out = edges + (size_t)map * plane + s_off;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint32_t e = s_pos[i];
+    if (threadIdx.x == 0) {
+        s_end[0] = 0;
+        for (int k = 0; k < 4; k++) s_end[k + 1] = s_end[k] + s_n[k];
+    }
+    __syncthreads();
+    uint2 *out = edges + (size_t)map * plane;
+    const int total = s_end[4];
+    int sub = 0;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        while (i >= s_end[sub + 1]) sub++;
+        const int li = i - s_end[sub];
+        const uint32_t e = s_pos[sub][li];
         const int x = e & 0xffff, y = e >> 16;
         int dx, dy;
         sobel_at(img, h, w, x, y, dx, dy);
@@ -98,7 +116,7 @@ __global__ void __launch_bounds__(256) k_edge_buckets(const MapSet ms, const uin
                 sy = __float2int_rn(__fdiv_rn(__fmul_rn(vy, 1024.0f), mag));
             }
         }
-        out[i] = make_uint2(e, (uint32_t)(sx & 0xffff) | ((uint32_t)sy << 16));   // (0,0) step = no vote
+        out[s_off[sub] + li] = make_uint2(e, (uint32_t)(sx & 0xffff) | ((uint32_t)sy << 16));   // (0,0) step = no vote
     }
 }
 
@@ -523,7 +541,7 @@ int hough_circles_maps(const MapSet &ms, int h, int w, float *mcirc, int32_t *mc
     bool al = (w & 3) == 0 && ((uintptr_t)state & 3) == 0;
     {
         ScopedSection sec(SEC_EDGE_LIST, st);
-        k_edge_buckets<<<dim3(nbx, nby, maps), 256, 0, st>>>(ms, state, h, w, al, edges, ecount, dir);
+        k_edge_buckets<<<dim3(cdiv(nbx, 2), cdiv(nby, 2), maps), 256, 0, st>>>(ms, state, h, w, al, edges, ecount, dir, nbx, nby);
         I2S_CHECK_LAUNCH("k_edge_buckets");
     }
     {

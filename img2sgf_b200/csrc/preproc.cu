@@ -237,6 +237,100 @@ template <int B> __global__ void __launch_bounds__(256) k_median(const uint8_t *
     }
 }
 
+// ---- 3x3 and 5x5: minimum-exchange selection networks on two pixels per register
+// (19 exchanges for 9 inputs, 99 for 25 inputs; N. Devillard's opt_med9 / opt_med25 orderings,
+// checked exhaustively with the 0-1 principle).  An exchange is one VIMNMX.U16x2 min + one max.
+__device__ __forceinline__ void cex(uint32_t &a, uint32_t &b)
+{
+    uint32_t lo = __vminu2(a, b);
+    b = __vmaxu2(a, b);
+    a = lo;
+}
+
+__device__ __forceinline__ uint32_t net_median9(uint32_t (&p)[9])
+{
+    cex(p[1], p[2]); cex(p[4], p[5]); cex(p[7], p[8]); cex(p[0], p[1]); cex(p[3], p[4]); cex(p[6], p[7]);
+    cex(p[1], p[2]); cex(p[4], p[5]); cex(p[7], p[8]); cex(p[0], p[3]); cex(p[5], p[8]); cex(p[4], p[7]);
+    cex(p[3], p[6]); cex(p[1], p[4]); cex(p[2], p[5]); cex(p[4], p[7]); cex(p[4], p[2]); cex(p[6], p[4]);
+    cex(p[4], p[2]);
+    return p[4];
+}
+
+__device__ __forceinline__ uint32_t net_median25(uint32_t (&p)[25])
+{
+    cex(p[0], p[1]); cex(p[3], p[4]); cex(p[2], p[4]); cex(p[2], p[3]); cex(p[6], p[7]); cex(p[5], p[7]);
+    cex(p[5], p[6]); cex(p[9], p[10]); cex(p[8], p[10]); cex(p[8], p[9]); cex(p[12], p[13]); cex(p[11], p[13]);
+    cex(p[11], p[12]); cex(p[15], p[16]); cex(p[14], p[16]); cex(p[14], p[15]); cex(p[18], p[19]); cex(p[17], p[19]);
+    cex(p[17], p[18]); cex(p[21], p[22]); cex(p[20], p[22]); cex(p[20], p[21]); cex(p[23], p[24]); cex(p[2], p[5]);
+    cex(p[3], p[6]); cex(p[0], p[6]); cex(p[0], p[3]); cex(p[4], p[7]); cex(p[1], p[7]); cex(p[1], p[4]);
+    cex(p[11], p[14]); cex(p[8], p[14]); cex(p[8], p[11]); cex(p[12], p[15]); cex(p[9], p[15]); cex(p[9], p[12]);
+    cex(p[13], p[16]); cex(p[10], p[16]); cex(p[10], p[13]); cex(p[20], p[23]); cex(p[17], p[23]); cex(p[17], p[20]);
+    cex(p[21], p[24]); cex(p[18], p[24]); cex(p[18], p[21]); cex(p[19], p[22]); cex(p[8], p[17]); cex(p[9], p[18]);
+    cex(p[0], p[18]); cex(p[0], p[9]); cex(p[10], p[19]); cex(p[1], p[19]); cex(p[1], p[10]); cex(p[11], p[20]);
+    cex(p[2], p[20]); cex(p[2], p[11]); cex(p[12], p[21]); cex(p[3], p[21]); cex(p[3], p[12]); cex(p[13], p[22]);
+    cex(p[4], p[22]); cex(p[4], p[13]); cex(p[14], p[23]); cex(p[5], p[23]); cex(p[5], p[14]); cex(p[15], p[24]);
+    cex(p[6], p[24]); cex(p[6], p[15]); cex(p[7], p[16]); cex(p[7], p[19]); cex(p[13], p[21]); cex(p[15], p[23]);
+    cex(p[7], p[13]); cex(p[7], p[15]); cex(p[1], p[9]); cex(p[3], p[11]); cex(p[5], p[17]); cex(p[11], p[17]);
+    cex(p[9], p[17]); cex(p[4], p[10]); cex(p[6], p[12]); cex(p[7], p[14]); cex(p[4], p[6]); cex(p[4], p[7]);
+    cex(p[12], p[14]); cex(p[10], p[14]); cex(p[6], p[7]); cex(p[10], p[12]); cex(p[6], p[10]); cex(p[6], p[17]);
+    cex(p[12], p[17]); cex(p[7], p[17]); cex(p[7], p[10]); cex(p[12], p[18]); cex(p[7], p[12]); cex(p[10], p[18]);
+    cex(p[12], p[20]); cex(p[10], p[20]); cex(p[10], p[12]);
+    return p[12];
+}
+
+template <int B> __global__ void __launch_bounds__(256) k_median_net(const uint8_t *__restrict__ src,
+                                                                     uint8_t *__restrict__ dst, int h, int w, bool al)
+{
+    static_assert(B == 3 || B == 5, "selection networks exist for 3x3 and 5x5");
+    constexpr int R = B / 2, HX = 4;
+    constexpr int SW = MT_W + 2 * HX, SH = MT_H + 2 * R;
+    __shared__ __align__(16) uint8_t s_in[SH * SW];
+    const size_t plane = (size_t)h * w;
+    const uint8_t *img = src + blockIdx.z * plane;
+    uint8_t *out = dst + blockIdx.z * plane;
+    const int x0 = blockIdx.x * MT_W, y0 = blockIdx.y * MT_H;
+    stage_tile_u8(s_in, SW, img, h, w, x0 - HX, y0 - R, SW, SH, BORDER_REPLICATE, al);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < MT_H * (MT_W / 4); idx += blockDim.x) {
+        int ty = idx / (MT_W / 4), gx = (idx - ty * (MT_W / 4)) * 4;
+        int y = y0 + ty, x = x0 + gx;
+        if (y >= h || x >= w) continue;
+        // e[dy][k] = (pixel x-R+k | pixel x-R+k+1 << 16): pair (x,x+1) uses k = 0..B-1, pair (x+2,x+3) k = 2..B+1
+        uint32_t e[B][B + 2];
+#pragma unroll
+        for (int dy = 0; dy < B; dy++) {
+            const uint32_t *rw = reinterpret_cast<const uint32_t *>(s_in + (ty + dy) * SW + gx);   // bytes x-4 .. x+7
+            uint32_t X[6];
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                uint32_t v = rw[j];
+                X[2 * j] = __byte_perm(v, 0, 0x4140);
+                X[2 * j + 1] = __byte_perm(v, 0, 0x4342);
+            }
+#pragma unroll
+            for (int k = 0; k < B + 2; k++) {
+                const int off = HX - R + k;                       // byte offset of the first pixel from x-4
+                e[dy][k] = (off & 1) ? __funnelshift_r(X[off >> 1], X[(off >> 1) + 1], 16) : X[off >> 1];
+            }
+        }
+        uint32_t pa, pb;
+        {
+            uint32_t p[B * B], q[B * B];
+#pragma unroll
+            for (int dy = 0; dy < B; dy++)
+#pragma unroll
+                for (int dx = 0; dx < B; dx++) { p[dy * B + dx] = e[dy][dx]; q[dy * B + dx] = e[dy][dx + 2]; }
+            if (B == 3) { pa = net_median9(reinterpret_cast<uint32_t (&)[9]>(p)); pb = net_median9(reinterpret_cast<uint32_t (&)[9]>(q)); }
+            else { pa = net_median25(reinterpret_cast<uint32_t (&)[25]>(p)); pb = net_median25(reinterpret_cast<uint32_t (&)[25]>(q)); }
+        }
+        uint32_t packed = (pa & 0xffu) | ((pa >> 8) & 0xff00u) | ((pb & 0xffu) << 16) | ((pb << 8) & 0xff000000u);
+        size_t o = (size_t)y * w + x;
+        if (al && x + 3 < w) *reinterpret_cast<uint32_t *>(out + o) = packed;
+        else
+            for (int k2 = 0; k2 < 4 && x + k2 < w; k2++) out[o + k2] = (uint8_t)(packed >> (8 * k2));
+    }
+}
+
 }  // namespace i2s
 
 using namespace i2s;
@@ -314,9 +408,9 @@ extern "C" int i2s_median(const uint8_t *src, uint8_t *dst, int n, int h, int w,
     if (b == 1) {
         I2S_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * h * w, cudaMemcpyDeviceToDevice, st));
     } else if (b == 3) {
-        k_median<3><<<grid, 256, 0, st>>>(src, dst, h, w, al);
+        k_median_net<3><<<grid, 256, 0, st>>>(src, dst, h, w, al);
     } else if (b == 5) {
-        k_median<5><<<grid, 256, 0, st>>>(src, dst, h, w, al);
+        k_median_net<5><<<grid, 256, 0, st>>>(src, dst, h, w, al);
     } else {
         k_median<7><<<grid, 256, 0, st>>>(src, dst, h, w, al);
     }
