@@ -13,7 +13,7 @@ the 384-byte records.  A "step" is one pass of the path over the rank's whole ba
 `value`  : images/s with the inputs already resident in HBM (CUDA events, max over ranks).
 `e2e`    : the same through the public API with HOST (pinned) buffers: H2D of every image and
            D2H of the records inside the timed region.
-`roofline`: Hough accumulator kernels (k_vote + k_peaks + accumulator clear), algorithmic bytes
+`roofline`: Hough accumulator kernels (k_edge_buckets + k_vote_peaks), algorithmic bytes
            10*W*H per HoughCircles call over their CUDA-event time inside the step.
 `cpu_baseline`: the reference's own cv2/sklearn calls (oracle/ref_replay.py) on all host cores,
            one process per core, on a bounded sample of the same workload.
@@ -38,7 +38,7 @@ if ROOT not in sys.path:
 
 WORKLOADS = {
     # name: (synth config, per-GPU batch, chunk)
-    "synth1024": ("synth1024", 1024, 64),
+    "synth1024": ("synth1024", 1024, 128),
     "synth2048": ("synth2048", 512, 16),
 }
 METRIC = "diagram images/sec"
@@ -165,7 +165,7 @@ def run_reference(args, rank, world):
     config, per_gpu, _ = WORKLOADS[args.workload]
     thr = synth.CONFIGS[config][3]
     cores = os.cpu_count() or 1
-    sample = max(2 * cores, 32) if args.cpu_images is None else args.cpu_images
+    sample = max(8 * cores, 64) if args.cpu_images is None else args.cpu_images
     rates, secs = [], []
     used = cores
     kind = "reference"
@@ -211,7 +211,7 @@ def run_ours(args, rank, world, local_rank):
     # CPU work first (fork-based pools must not run after CUDA is initialised)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = max(2 * cores, 32) if args.cpu_images is None else args.cpu_images
+        sample = max(8 * cores, 64) if args.cpu_images is None else args.cpu_images
         rate, n, used, kind, dt = cpu_reference_rate(config, thr, sample, cores)
         cpu = {"value": rate, "unit": UNIT, "cores": used, "kind": kind,
                "sample": f"{n} images of the workload, one single-threaded process per core, {dt:.1f} s wall "
@@ -324,7 +324,7 @@ def run_ours(args, rank, world, local_rank):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         sections = {lib.i2s_profile_section_name(i).decode(): {"ms_per_step": ms[i] / args.steps, "launches": int(cnt[i])}
                     for i in range(nsec) if cnt[i]}
-        acc_ms = sum(sections.get(k, {"ms_per_step": 0})["ms_per_step"] for k in ("vote", "peaks", "acc_clear"))
+        acc_ms = sum(sections.get(k, {"ms_per_step": 0})["ms_per_step"] for k in ("edge_list", "vote"))
         calls_per_step = 8 * per_gpu                     # unique HoughCircles inputs per image (SURVEY Fact 2)
         alg_bytes = 10.0 * size * size * calls_per_step  # 10*P per call: image+edges read, int32 acc store+load
         achieved = alg_bytes / (acc_ms / 1000.0) / 1e9 if acc_ms > 0 else None
@@ -337,7 +337,7 @@ def run_ours(args, rank, world, local_rank):
                        "chunk": chunk, "parallelism": f"image shards x{world}, all-gather of 384-byte records",
                        "l2": "inputs (3 MiB/image x batch) far larger than the 126 MB L2; no flush needed"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "hough_accum (acc clear + k_vote + k_peaks), 8 calls/image",
+            "roofline": {"bound": "hbm", "kernel": "hough_accum (k_edge_buckets + k_vote_peaks: vote + peak find fused), 8 calls/image",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",

@@ -339,7 +339,7 @@ extern "C" const char *i2s_last_error(void) { return i2s::g_err; }
 extern "C" int i2s_version(void) { return 100; }
 extern "C" void i2s_default_limits(i2s_limits_t *lim)
 {
-    lim->cand_cap = 8192;
+    lim->cand_cap = 4096;
     lim->circle_cap = 4096;
     lim->line_cap = 1024;
     lim->hyst_passes = 8;

@@ -2,7 +2,8 @@
 import csv, subprocess, sys
 rep, kern = sys.argv[1], sys.argv[2]
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 16
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{kern}", "--launch-count", "1"],
+skip = sys.argv[4] if len(sys.argv) > 4 else "0"
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{kern}", "--launch-skip", skip, "--launch-count", "1"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 his = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
