@@ -108,7 +108,7 @@ __device__ __forceinline__ void py_slice(int len, int &lo, int &hi)
     if (lo > len) lo = len;
 }
 
-__global__ void __launch_bounds__(256) k_classify(const uint8_t *__restrict__ grey, int h, int w,
+__global__ void __launch_bounds__(512) k_classify(const uint8_t *__restrict__ grey, int h, int w,
                                                   const float *__restrict__ circles, const int32_t *__restrict__ counts,
                                                   int circle_cap, const i2s_grid_t *__restrict__ grids, int black_thr,
                                                   i2s_record_t *records, double *brightness, const int32_t *status)
@@ -211,7 +211,7 @@ int classify_stones(const uint8_t *grey, int n, int h, int w, const float *circl
                     double *brightness, const int32_t *status, cudaStream_t st)
 {
     ScopedSection sec(SEC_CLASSIFY, st);
-    k_classify<<<n, 256, 0, st>>>(grey, h, w, circles, counts, circle_cap, grids, black_threshold, records, brightness,
+    k_classify<<<n, 512, 0, st>>>(grey, h, w, circles, counts, circle_cap, grids, black_threshold, records, brightness,
                                   status);
     I2S_CHECK_LAUNCH("k_classify");
     return I2S_OK;

@@ -348,37 +348,52 @@ __global__ void __launch_bounds__(RW * 32) k_radius(const uint2 *__restrict__ ed
 
 // ------------------------------------------------------------------ K7b: total-order sort + greedy minDist
 // One block per map: bitonic sort of the packed keys (support desc, radius desc, x asc, y asc),
-// then warp 0 runs the sequential suppression (kept iff >= 10 px from every kept circle).
+// then warp 0 runs the sequential suppression (kept iff >= 10 px from every kept circle).  Kept
+// circles are hashed into a grid of cells at least 16 px wide, so a candidate only has to be
+// compared with the chains of its 3x3 cell neighbourhood (lanes 0..8, one cell each).
 __global__ void __launch_bounds__(256) k_circles_finish(const unsigned long long *__restrict__ est,
-                                                        const int32_t *__restrict__ nest, int cand_cap, float *circ,
+                                                        const int32_t *__restrict__ nest, int cand_cap, int np2cap,
+                                                        int cshift, int cells_x, int cells_y, float *circ,
                                                         int32_t *ncirc, int circle_cap, int32_t *status, int n_images)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    unsigned long long *keys = reinterpret_cast<unsigned long long *>(s_raw);
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(s_raw);          // np2cap
+    short2 *kept = reinterpret_cast<short2 *>(keys + np2cap);                          // np2cap
+    uint16_t *next = reinterpret_cast<uint16_t *>(kept + np2cap);                      // np2cap
+    uint16_t *head = next + np2cap;                                                    // cells_x * cells_y
     const int map = blockIdx.x;
     int n = min(nest[map], cand_cap);
     int np2 = 1;
     while (np2 < n) np2 <<= 1;
-    short2 *kept = reinterpret_cast<short2 *>(keys + np2);
     for (int i = threadIdx.x; i < np2; i += blockDim.x)
         keys[i] = i < n ? est[(size_t)map * cand_cap + i] : ~0ull;
+    for (int i = threadIdx.x; i < cells_x * cells_y; i += blockDim.x) head[i] = 0xffff;
     __syncthreads();
     bitonic_sort_block(keys, np2);
     if (threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
+    const int ddx = lane % 3 - 1, ddy = lane / 3 - 1;      // lanes 0..8: the 3x3 cell neighbourhood
     int nk = 0;
     float *out = circ + (size_t)map * circle_cap * 3;
     for (int i = 0; i < n; i++) {
         unsigned long long k = keys[i];
         int x = (int)((k >> 14) & 0x3fff), y = (int)(k & 0x3fff);
+        const int cx = x >> cshift, cy = y >> cshift;
         bool clash = false;
-        for (int j = lane; j < nk; j += 32) {
-            int dx = kept[j].x - x, dy = kept[j].y - y;
-            clash |= dx * dx + dy * dy < 100;
+        if (lane < 9) {
+            int ncx = cx + ddx, ncy = cy + ddy;
+            if (ncx >= 0 && ncx < cells_x && ncy >= 0 && ncy < cells_y) {
+                for (int j = head[ncy * cells_x + ncx]; j != 0xffff; j = next[j]) {
+                    int dx = kept[j].x - x, dy = kept[j].y - y;
+                    clash |= dx * dx + dy * dy < 100;
+                }
+            }
         }
         if (__any_sync(0xffffffffu, clash)) continue;
         if (lane == 0) {
             kept[nk] = make_short2((short)x, (short)y);
+            next[nk] = head[cy * cells_x + cx];
+            head[cy * cells_x + cx] = (uint16_t)nk;
             if (nk < circle_cap) {
                 out[3 * nk] = (float)x + 0.5f;
                 out[3 * nk + 1] = (float)y + 0.5f;
@@ -559,9 +574,13 @@ int hough_circles_maps(const MapSet &ms, int h, int w, float *mcirc, int32_t *mc
     ScopedSection sec(SEC_CIRCLES_FINISH, st);
     int np2 = 1;
     while (np2 < lim.cand_cap) np2 <<= 1;
-    size_t smem = (size_t)np2 * 8 + (size_t)np2 * 4;
+    int cshift = 4;                                            // cells of >= 16 px (> minDist), at most 16384 of them
+    while ((size_t)((w >> cshift) + 1) * ((h >> cshift) + 1) > 16384) cshift++;
+    const int cells_x = (w >> cshift) + 1, cells_y = (h >> cshift) + 1;
+    size_t smem = (size_t)np2 * (8 + 4 + 2) + (size_t)cells_x * cells_y * 2;
     I2S_CUDA(cudaFuncSetAttribute(k_circles_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_circles_finish<<<maps, 256, smem, st>>>(est, nest, lim.cand_cap, mcirc, mcount, lim.circle_cap, status, ms.n);
+    k_circles_finish<<<maps, 256, smem, st>>>(est, nest, lim.cand_cap, np2, cshift, cells_x, cells_y, mcirc, mcount,
+                                              lim.circle_cap, status, ms.n);
     I2S_CHECK_LAUNCH("k_circles_finish");
     return I2S_OK;
 }

@@ -342,7 +342,7 @@ extern "C" void i2s_default_limits(i2s_limits_t *lim)
     lim->cand_cap = 4096;
     lim->circle_cap = 4096;
     lim->line_cap = 1024;
-    lim->hyst_passes = 8;
+    lim->hyst_passes = 5;
 }
 
 extern "C" int i2s_grey(const uint8_t *rgb, uint8_t *grey, int n, int h, int w, void *stream)
