@@ -7,58 +7,59 @@
 // bit1 = edge (strong, or weak reached from a strong one).  Final edge <=> bit1.
 #include "canny.cuh"
 #include "profile.cuh"
+#include "tma.cuh"
 
 namespace i2s {
 
 // ------------------------------------------------------------------ Sobel + NMS
 constexpr int NT = 64;                 // output tile (NT x NT), 256 threads
-constexpr int NS_W = NT + 8;           // staged source: x halo 4 (aligned), y halo 2
-constexpr int NS_H = NT + 4;
 constexpr int NM = NT + 2;             // magnitude rows (tile + 1-px ring)
-constexpr int NMP = NS_W;              // magnitude row pitch = staged pitch (column index = staged column)
 
 template <int CH>
 __global__ void __launch_bounds__(256) k_sobel_nms(const MapSet ms, uint8_t *__restrict__ state,
-                                                   int h, int w, int low, int high, bool al)
+                                                   int h, int w, int low, int high, bool al, bool bulk)
 {
-    __shared__ __align__(16) uint8_t s_src[NS_H * NS_W * CH];
-    __shared__ __align__(16) int s_dxy[NM * NMP];          // dx | dy << 16 (two's complement halves)
-    __shared__ __align__(16) uint16_t s_mag[NM * NMP];
+    // staged source: y halo 2; x halo 16 for the single-channel kernel (rows are then 16-byte aligned
+    // bulk copies), 4 for the 3-channel one.  Gradient arrays are indexed [mr][staged column].
+    constexpr int HXL = (CH == 1) ? 16 : 4;
+    constexpr int SW_ = NT + 2 * HXL, SH_ = NT + 4, MP = SW_;
+    __shared__ __align__(128) uint8_t s_src[SH_ * SW_ * CH];
+    __shared__ __align__(16) int s_dxy[NM * MP];          // dx | dy << 16 (two's complement halves)
+    __shared__ __align__(16) uint16_t s_mag[NM * MP];
+    __shared__ uint64_t s_bar;
     const size_t plane = (size_t)h * w;
     const uint8_t *img = ms.plane(blockIdx.z, plane * CH);
     const int x0 = blockIdx.x * NT, y0 = blockIdx.y * NT;
 
     if (CH == 1) {
-        stage_tile_u8(s_src, NS_W, img, h, w, x0 - 4, y0 - 2, NS_W, NS_H, BORDER_REPLICATE, al);
+        stage_tile_bulk(s_src, img, h, w, x0 - HXL, y0 - 2, SW_, SH_, BORDER_REPLICATE, bulk, al, &s_bar);
     } else {
-        for (int idx = threadIdx.x; idx < NS_H * NS_W; idx += blockDim.x) {
-            int ty = idx / NS_W, tx = idx - ty * NS_W;
+        for (int idx = threadIdx.x; idx < SH_ * SW_; idx += blockDim.x) {
+            int ty = idx / SW_, tx = idx - ty * SW_;
             int y = border_index(y0 - 2 + ty, h, BORDER_REPLICATE);
-            int x = border_index(x0 - 4 + tx, w, BORDER_REPLICATE);
+            int x = border_index(x0 - HXL + tx, w, BORDER_REPLICATE);
             const uint8_t *p = img + ((size_t)y * w + x) * CH;
 #pragma unroll
             for (int c = 0; c < CH; c++) s_src[idx * CH + c] = __ldg(p + c);
         }
+        __syncthreads();
     }
-    __syncthreads();
 
-    // gradients for rows y0-1 .. y0+NT (the tile and its 1-px ring) at every staged column;
-    // magnitude is 0 outside the image.  Array index = mr * NMP + staged column.
+    // gradients for rows y0-1 .. y0+NT (the tile and its 1-px ring); magnitude is 0 outside the image
     if (CH == 1) {
         // four pixels per thread from three staged rows: column sums v = t + 2m + b and column
         // differences d = b - t give dx_i = v_{i+1} - v_{i-1}, dy_i = d_{i-1} + 2 d_i + d_{i+1}
-        constexpr int G = NS_W / 4;
-        for (int idx = threadIdx.x; idx < NM * G; idx += blockDim.x) {
-            const int mr = idx / G, g = idx - mr * G;
+        constexpr int G = SW_ / 4, G0 = HXL / 4 - 1, GN = NT / 4 + 2;     // groups holding columns x0-4 .. x0+NT+3
+        for (int idx = threadIdx.x; idx < NM * GN; idx += blockDim.x) {
+            const int mr = idx / GN, g = G0 + idx - mr * GN;
             const int y = y0 - 1 + mr;
-            const uint32_t *r0 = reinterpret_cast<const uint32_t *>(s_src + mr * NS_W);
+            const uint32_t *r0 = reinterpret_cast<const uint32_t *>(s_src + mr * SW_);
             const uint32_t *r1 = r0 + G, *r2 = r1 + G;
-            const int ga = g > 0 ? g - 1 : 0, gc = g < G - 1 ? g + 1 : G - 1;   // clamped: only unused columns see it
             int v[6], d[6];
             {
-                const uint32_t ta = r0[ga], tb = r0[g], tc = r0[gc];
-                const uint32_t ma = r1[ga], mb = r1[g], mc = r1[gc];
-                const uint32_t ba = r2[ga], bb = r2[g], bc = r2[gc];
+                const uint32_t ta = r0[g - 1], tb = r0[g], tc = r0[g + 1];
+                const uint32_t ma = r1[g - 1], mb = r1[g], mc = r1[g + 1];
+                const uint32_t ba = r2[g - 1], bb = r2[g], bc = r2[g + 1];
                 int t, m, b;
                 t = ta >> 24; m = ma >> 24; b = ba >> 24; v[0] = t + 2 * m + b; d[0] = b - t;
 #pragma unroll
@@ -68,28 +69,31 @@ __global__ void __launch_bounds__(256) k_sobel_nms(const MapSet ms, uint8_t *__r
                 }
                 t = tc & 0xff; m = mc & 0xff; b = bc & 0xff; v[5] = t + 2 * m + b; d[5] = b - t;
             }
+            const int xg = x0 - HXL + 4 * g;
+            const bool row_in = y >= 0 && y < h;
+            const bool all_in = row_in && xg >= 0 && xg + 3 < w;
             int4 oxy;
             uint32_t om[2] = {0, 0};
             int *po = &oxy.x;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int dx = v[i + 2] - v[i], dy = d[i] + 2 * d[i + 1] + d[i + 2];
-                const int x = x0 - 4 + 4 * g + i;
-                const int mg = (x >= 0 && x < w && y >= 0 && y < h) ? abs(dx) + abs(dy) : 0;
+                const bool in = all_in || (row_in && xg + i >= 0 && xg + i < w);
+                const int mg = in ? abs(dx) + abs(dy) : 0;
                 po[i] = (int)((uint32_t)(dx & 0xffff) | ((uint32_t)dy << 16));
                 om[i >> 1] |= (uint32_t)mg << (16 * (i & 1));
             }
-            *reinterpret_cast<int4 *>(s_dxy + mr * NMP + 4 * g) = oxy;
-            *reinterpret_cast<uint2 *>(s_mag + mr * NMP + 4 * g) = make_uint2(om[0], om[1]);
+            *reinterpret_cast<int4 *>(s_dxy + mr * MP + 4 * g) = oxy;
+            *reinterpret_cast<uint2 *>(s_mag + mr * MP + 4 * g) = make_uint2(om[0], om[1]);
         }
     } else {
-        for (int idx = threadIdx.x; idx < NM * NMP; idx += blockDim.x) {
-            const int mr = idx / NMP, col = idx - mr * NMP;
-            const int x = x0 - 4 + col, y = y0 - 1 + mr;
+        for (int idx = threadIdx.x; idx < NM * MP; idx += blockDim.x) {
+            const int mr = idx / MP, col = idx - mr * MP;
+            const int x = x0 - HXL + col, y = y0 - 1 + mr;
             int bdx = 0, bdy = 0, bm = 0;
-            if (col >= 1 && col < NS_W - 1 && x >= 0 && x < w && y >= 0 && y < h) {
-                const uint8_t *c = s_src + ((mr + 1) * NS_W + col) * CH;   // centre sample
-                constexpr int RS = NS_W * CH;
+            if (col >= 1 && col < SW_ - 1 && x >= 0 && x < w && y >= 0 && y < h) {
+                const uint8_t *c = s_src + ((mr + 1) * SW_ + col) * CH;   // centre sample
+                constexpr int RS = SW_ * CH;
 #pragma unroll
                 for (int ch = 0; ch < CH; ch++) {
                     int p00 = c[-RS - CH + ch], p01 = c[-RS + ch], p02 = c[-RS + CH + ch];
@@ -114,7 +118,7 @@ __global__ void __launch_bounds__(256) k_sobel_nms(const MapSet ms, uint8_t *__r
         uint32_t packed = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const int c = (ty + 1) * NMP + gx + k + 4;
+            const int c = (ty + 1) * MP + gx + k + HXL;
             int m = s_mag[c];
             uint32_t st = 0;
             if (m > low) {
@@ -126,10 +130,10 @@ __global__ void __launch_bounds__(256) k_sobel_nms(const MapSet ms, uint8_t *__r
                 if (ay < t22) keep = m > s_mag[c - 1] && m >= s_mag[c + 1];
                 else {
                     int t67 = t22 + (ax << 16);
-                    if (ay > t67) keep = m > s_mag[c - NMP] && m >= s_mag[c + NMP];
+                    if (ay > t67) keep = m > s_mag[c - MP] && m >= s_mag[c + MP];
                     else {
                         int s = (xs ^ ys) < 0 ? -1 : 1;
-                        keep = m > s_mag[c - NMP - s] && m > s_mag[c + NMP + s];
+                        keep = m > s_mag[c - MP - s] && m > s_mag[c + MP + s];
                     }
                 }
                 if (keep) st = m > high ? 3u : 1u;
@@ -288,8 +292,9 @@ int canny_states(const MapSet &ms, int channels, uint8_t *state, int h, int w, i
     dim3 g1(cdiv(w, NT), cdiv(h, NT), maps);
     {
     ScopedSection sec(SEC_SOBEL_NMS, st);
-    if (channels == 1) k_sobel_nms<1><<<g1, 256, 0, st>>>(ms, state, h, w, low, high, al);
-    else k_sobel_nms<3><<<g1, 256, 0, st>>>(ms, state, h, w, low, high, al);
+    bool bulk = (w & 15) == 0 && ms.aligned16();
+    if (channels == 1) k_sobel_nms<1><<<g1, 256, 0, st>>>(ms, state, h, w, low, high, al, bulk);
+    else k_sobel_nms<3><<<g1, 256, 0, st>>>(ms, state, h, w, low, high, al, false);
     I2S_CHECK_LAUNCH("k_sobel_nms");
     }
     return hysteresis(state, maps, ms.n, h, w, passes, status, scratch, st);

@@ -72,6 +72,12 @@ struct MapSet {
         for (int k = 0; k < count; k++) a |= (uintptr_t)src[k];
         return (a & 3) == 0;
     }
+    bool aligned16() const
+    {
+        uintptr_t a = 0;
+        for (int k = 0; k < count; k++) a |= (uintptr_t)src[k];
+        return (a & 15) == 0;
+    }
     static MapSet single(const uint8_t *p, int n)
     {
         MapSet ms{};

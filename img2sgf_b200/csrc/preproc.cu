@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include "common.cuh"
 #include "profile.cuh"
+#include "tma.cuh"
 
 namespace i2s {
 
@@ -78,20 +79,21 @@ __global__ void __launch_bounds__(256) k_contrast(const uint8_t *__restrict__ rg
 // Output tile 128 x 32 per 256-thread block.  Input staged with a halo of 4 (x) / 3 (y),
 // REFLECT_101.  Horizontal pass keeps Q8 sums (<= 65280, u16) for the three kernels in
 // shared memory, vertical pass accumulates Q16 and rounds once.
-constexpr int GT_W = 128, GT_H = 32, GH_X = 4, GH_Y = 3;
-constexpr int GS_W = GT_W + 2 * GH_X;   // 136
+constexpr int GT_W = 128, GT_H = 32, GH_X = 16, GH_Y = 3;   // x halo 16: bulk-copy rows are 16-byte aligned
+constexpr int GS_W = GT_W + 2 * GH_X;   // 160
 constexpr int GS_H = GT_H + 2 * GH_Y;   // 38
 
 __global__ void __launch_bounds__(256) k_gauss357(const uint8_t *__restrict__ src, uint8_t *__restrict__ d3,
-                                                  uint8_t *__restrict__ d5, uint8_t *__restrict__ d7, int h, int w, bool al)
+                                                  uint8_t *__restrict__ d5, uint8_t *__restrict__ d7, int h, int w, bool al,
+                                                  bool bulk)
 {
-    __shared__ __align__(16) uint8_t s_in[GS_H * GS_W];
+    __shared__ __align__(128) uint8_t s_in[GS_H * GS_W];
+    __shared__ uint64_t s_bar;
     __shared__ __align__(16) uint16_t s_h[3][GS_H][GT_W];
     const size_t plane = (size_t)h * w;
     const uint8_t *img = src + blockIdx.z * plane;
     const int x0 = blockIdx.x * GT_W, y0 = blockIdx.y * GT_H;
-    stage_tile_u8(s_in, GS_W, img, h, w, x0 - GH_X, y0 - GH_Y, GS_W, GS_H, BORDER_REFLECT101, al);
-    __syncthreads();
+    stage_tile_bulk(s_in, img, h, w, x0 - GH_X, y0 - GH_Y, GS_W, GS_H, BORDER_REFLECT101, bulk, al, &s_bar);
     for (int idx = threadIdx.x; idx < GS_H * GT_W; idx += blockDim.x) {
         int ty = idx / GT_W, tx = idx - ty * GT_W;
         const uint8_t *p = s_in + ty * GS_W + tx + GH_X;
@@ -147,22 +149,23 @@ __global__ void __launch_bounds__(256) k_gauss357(const uint8_t *__restrict__ sr
 constexpr int MT_W = 64, MT_H = 32;
 
 template <int B> __global__ void __launch_bounds__(256) k_median(const uint8_t *__restrict__ src,
-                                                                 uint8_t *__restrict__ dst, int h, int w, bool al)
+                                                                 uint8_t *__restrict__ dst, int h, int w, bool al,
+                                                                 bool bulk)
 {
-    constexpr int R = B / 2, HX = 4;                 // x halo rounded up to 4 for aligned staging
+    constexpr int R = B / 2, HX = 16;                // x halo 16: bulk-copy rows are 16-byte aligned
     constexpr int SW = MT_W + 2 * HX, SH = MT_H + 2 * R;
     constexpr int GW = (SW + 31) / 32;               // 32-pixel groups per tile row
     constexpr int F = B + 3;                         // window columns of 4 adjacent pixels
     constexpr int RPW = 32 / F;                      // window rows packed per 32-bit word
     constexpr int NW = (B + RPW - 1) / RPW;          // words per window
-    __shared__ __align__(16) uint8_t s_in[SH * SW];
+    __shared__ __align__(128) uint8_t s_in[SH * SW];
     __shared__ uint32_t s_bits[8][SH][GW + 1];
+    __shared__ uint64_t s_bar;
     const size_t plane = (size_t)h * w;
     const uint8_t *img = src + blockIdx.z * plane;
     uint8_t *out = dst + blockIdx.z * plane;
     const int x0 = blockIdx.x * MT_W, y0 = blockIdx.y * MT_H;
-    stage_tile_u8(s_in, SW, img, h, w, x0 - HX, y0 - R, SW, SH, BORDER_REPLICATE, al);
-    __syncthreads();
+    stage_tile_bulk(s_in, img, h, w, x0 - HX, y0 - R, SW, SH, BORDER_REPLICATE, bulk, al, &s_bar);
     {   // bit planes: s_bits[b][row][g] bit i = bit b of tile pixel (row, 32 g + i)
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         for (int u = warp; u < SH * GW; u += 8) {
@@ -279,18 +282,19 @@ __device__ __forceinline__ uint32_t net_median25(uint32_t (&p)[25])
 }
 
 template <int B> __global__ void __launch_bounds__(256) k_median_net(const uint8_t *__restrict__ src,
-                                                                     uint8_t *__restrict__ dst, int h, int w, bool al)
+                                                                     uint8_t *__restrict__ dst, int h, int w, bool al,
+                                                                     bool bulk)
 {
     static_assert(B == 3 || B == 5, "selection networks exist for 3x3 and 5x5");
-    constexpr int R = B / 2, HX = 4;
+    constexpr int R = B / 2, HX = 16;
     constexpr int SW = MT_W + 2 * HX, SH = MT_H + 2 * R;
-    __shared__ __align__(16) uint8_t s_in[SH * SW];
+    __shared__ __align__(128) uint8_t s_in[SH * SW];
+    __shared__ uint64_t s_bar;
     const size_t plane = (size_t)h * w;
     const uint8_t *img = src + blockIdx.z * plane;
     uint8_t *out = dst + blockIdx.z * plane;
     const int x0 = blockIdx.x * MT_W, y0 = blockIdx.y * MT_H;
-    stage_tile_u8(s_in, SW, img, h, w, x0 - HX, y0 - R, SW, SH, BORDER_REPLICATE, al);
-    __syncthreads();
+    stage_tile_bulk(s_in, img, h, w, x0 - HX, y0 - R, SW, SH, BORDER_REPLICATE, bulk, al, &s_bar);
     for (int idx = threadIdx.x; idx < MT_H * (MT_W / 4); idx += blockDim.x) {
         int ty = idx / (MT_W / 4), gx = (idx - ty * (MT_W / 4)) * 4;
         int y = y0 + ty, x = x0 + gx;
@@ -299,7 +303,7 @@ template <int B> __global__ void __launch_bounds__(256) k_median_net(const uint8
         uint32_t e[B][B + 2];
 #pragma unroll
         for (int dy = 0; dy < B; dy++) {
-            const uint32_t *rw = reinterpret_cast<const uint32_t *>(s_in + (ty + dy) * SW + gx);   // bytes x-4 .. x+7
+            const uint32_t *rw = reinterpret_cast<const uint32_t *>(s_in + (ty + dy) * SW + gx + HX - 4);   // bytes x-4 .. x+7
             uint32_t X[6];
 #pragma unroll
             for (int j = 0; j < 3; j++) {
@@ -309,7 +313,7 @@ template <int B> __global__ void __launch_bounds__(256) k_median_net(const uint8
             }
 #pragma unroll
             for (int k = 0; k < B + 2; k++) {
-                const int off = HX - R + k;                       // byte offset of the first pixel from x-4
+                const int off = 4 - R + k;                        // byte offset of the first pixel from x-4
                 e[dy][k] = (off & 1) ? __funnelshift_r(X[off >> 1], X[(off >> 1) + 1], 16) : X[off >> 1];
             }
         }
@@ -392,7 +396,8 @@ extern "C" int i2s_gauss357(const uint8_t *src, uint8_t *dst3, uint8_t *dst5, ui
     bool al = (w & 3) == 0 && (((uintptr_t)src | (uintptr_t)dst3 | (uintptr_t)dst5 | (uintptr_t)dst7) & 3) == 0;
     dim3 grid(cdiv(w, GT_W), cdiv(h, GT_H), n);
     ScopedSection sec(SEC_GAUSS, (cudaStream_t)stream);
-    k_gauss357<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst3, dst5, dst7, h, w, al);
+    bool bulk = (w & 15) == 0 && ((uintptr_t)src & 15) == 0;
+    k_gauss357<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst3, dst5, dst7, h, w, al, bulk);
     I2S_CHECK_LAUNCH("k_gauss357");
     return I2S_OK;
 }
@@ -405,14 +410,15 @@ extern "C" int i2s_median(const uint8_t *src, uint8_t *dst, int n, int h, int w,
     dim3 grid(cdiv(w, MT_W), cdiv(h, MT_H), n);
     ScopedSection sec(SEC_MEDIAN, st);
     bool al = (w & 3) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 3) == 0;
+    bool bulk = (w & 15) == 0 && ((uintptr_t)src & 15) == 0;
     if (b == 1) {
         I2S_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * h * w, cudaMemcpyDeviceToDevice, st));
     } else if (b == 3) {
-        k_median_net<3><<<grid, 256, 0, st>>>(src, dst, h, w, al);
+        k_median_net<3><<<grid, 256, 0, st>>>(src, dst, h, w, al, bulk);
     } else if (b == 5) {
-        k_median_net<5><<<grid, 256, 0, st>>>(src, dst, h, w, al);
+        k_median_net<5><<<grid, 256, 0, st>>>(src, dst, h, w, al, bulk);
     } else {
-        k_median<7><<<grid, 256, 0, st>>>(src, dst, h, w, al);
+        k_median<7><<<grid, 256, 0, st>>>(src, dst, h, w, al, bulk);
     }
     I2S_CHECK_LAUNCH("k_median");
     return I2S_OK;
