@@ -230,7 +230,7 @@ def run_ours(args, rank, world, local_rank):
     host = torch.empty((per_gpu, size, size, 3), dtype=torch.uint8).pin_memory()
     host.copy_(torch.from_numpy(grey)[..., None].expand(-1, -1, -1, 3))
     dev = host.cuda()
-    runner = B.BatchRunner(size, size, chunk)
+    runner = B.BatchRunner(size, size, chunk, streams=args.streams)
     records = torch.zeros((per_gpu, B.RECORD_BYTES), dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -334,7 +334,7 @@ def run_ours(args, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32/f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {size}x{size} synthetic diagrams, full path RGB->board record, "
                                    f"line threshold {thr}", "images_per_gpu": per_gpu, "global_batch": total,
-                       "chunk": chunk, "parallelism": f"image shards x{world}, all-gather of 384-byte records",
+                       "chunk": chunk, "streams": args.streams, "parallelism": f"image shards x{world}, all-gather of 384-byte records",
                        "l2": "inputs (3 MiB/image x batch) far larger than the 126 MB L2; no flush needed"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "hough_accum (k_edge_buckets + k_vote_peaks: vote + peak find fused), 8 calls/image",
@@ -360,6 +360,7 @@ def main():
     ap.add_argument("--workload", default="synth1024", choices=sorted(WORKLOADS))
     ap.add_argument("--per-gpu", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--streams", type=int, default=1)
     ap.add_argument("--cpu-images", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -86,11 +86,17 @@ class Engine:
 
 
 class BatchRunner:
-    """Runs `total` same-sized images through an Engine in chunks of `chunk` images."""
+    """Runs `total` same-sized images through Engines in chunks of `chunk` images.
 
-    def __init__(self, h: int, w: int, chunk: int, limits: N.Limits | None = None):
+    With `streams` > 1 consecutive chunks alternate between that many CUDA streams (one Engine and
+    workspace each), so the short low-occupancy kernels at the end of one chunk (circle sort and
+    suppression, line peaks, clustering, classification) overlap the wide kernels of the next."""
+
+    def __init__(self, h: int, w: int, chunk: int, limits: N.Limits | None = None, streams: int = 1):
         self.h, self.w, self.chunk = h, w, chunk
-        self.engine = Engine(chunk, h, w, limits)
+        self.engines = [Engine(chunk, h, w, limits) for _ in range(max(1, streams))]
+        self.engine = self.engines[0]
+        self.streams = [torch.cuda.Stream() for _ in self.engines] if streams > 1 else None
 
     def run(self, rgb: torch.Tensor, line_threshold: int, black_threshold: int = 128,
             records: torch.Tensor | None = None) -> torch.Tensor:
@@ -98,9 +104,21 @@ class BatchRunner:
         total = rgb.shape[0]
         if records is None:
             records = torch.zeros((total, RECORD_BYTES), dtype=torch.uint8, device="cuda")
-        for s in range(0, total, self.chunk):
+        cur = torch.cuda.current_stream()
+        if self.streams:
+            for st in self.streams:
+                st.wait_stream(cur)
+        for k, s in enumerate(range(0, total, self.chunk)):
             e = min(total, s + self.chunk)
-            self.engine.run(rgb[s:e], line_threshold, black_threshold, n=e - s, records_out=records[s:e])
+            eng = self.engines[k % len(self.engines)]
+            if self.streams:
+                with torch.cuda.stream(self.streams[k % len(self.streams)]):
+                    eng.run(rgb[s:e], line_threshold, black_threshold, n=e - s, records_out=records[s:e])
+            else:
+                eng.run(rgb[s:e], line_threshold, black_threshold, n=e - s, records_out=records[s:e])
+        if self.streams:
+            for st in self.streams:
+                cur.wait_stream(st)
         return records
 
     def launches_per_chunk(self) -> int:

@@ -50,19 +50,29 @@ __global__ void __launch_bounds__(256) k_edge_buckets(const MapSet ms, const uin
     const int lane = threadIdx.x & 31;
     if (threadIdx.x < 4) s_n[threadIdx.x] = 0;
     __syncthreads();
+    // all four state words of this thread first (independent loads in flight), then the compaction
+    uint32_t vv[4];
+#pragma unroll
+    for (int sub = 0; sub < 4; sub++) {
+        const int bxx = blockIdx.x * 2 + (sub & 1), byy = blockIdx.y * 2 + (sub >> 1);
+        const int ty = threadIdx.x / (EB / 4), gx = (threadIdx.x % (EB / 4)) * 4;
+        const int y = byy * EB + ty, x = bxx * EB + gx;
+        uint32_t v = 0;
+        if (bxx < nbx && byy < nby && y < h && x < w) {
+            const uint8_t *p = stm + (size_t)y * w + x;
+            if (al && x + 3 < w) v = __ldg(reinterpret_cast<const uint32_t *>(p));
+            else
+                for (int k = 0; k < 4 && x + k < w; k++) v |= (uint32_t)__ldg(p + k) << (8 * k);
+        }
+        vv[sub] = v;
+    }
 #pragma unroll
     for (int sub = 0; sub < 4; sub++) {
         const int bxx = blockIdx.x * 2 + (sub & 1), byy = blockIdx.y * 2 + (sub >> 1);
         if (bxx >= nbx || byy >= nby) continue;                      // block-uniform
         const int ty = threadIdx.x / (EB / 4), gx = (threadIdx.x % (EB / 4)) * 4;
         const int y = byy * EB + ty, x = bxx * EB + gx;
-        uint32_t v = 0;
-        if (y < h && x < w) {
-            const uint8_t *p = stm + (size_t)y * w + x;
-            if (al && x + 3 < w) v = __ldg(reinterpret_cast<const uint32_t *>(p));
-            else
-                for (int k = 0; k < 4 && x + k < w; k++) v |= (uint32_t)__ldg(p + k) << (8 * k);
-        }
+        uint32_t v = vv[sub];
         v &= 0x02020202u;
         const int nb = __popc(v);                                    // 0..4 edge pixels in this word
         const uint32_t b0 = __ballot_sync(0xffffffffu, nb & 1), b1 = __ballot_sync(0xffffffffu, nb & 2),
@@ -163,7 +173,7 @@ __global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks(const uint2 *__rest
         int b = threadIdx.x;
         int2 d = dir[((size_t)map * nby + by0 + b / nbw) * nbx + bx0 + b % nbw];
         s_boff[b] = d.x;
-        s_bend[b + 1] = 2 * d.y;                                     // two rays per edge pixel
+        s_bend[b + 1] = d.y;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -172,18 +182,18 @@ __global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks(const uint2 *__rest
         for (int b = 0; b < nb; b++) { run += s_bend[b + 1]; s_bend[b + 1] = run; }
     }
     __syncthreads();
-    const int items = s_bend[nb];
+    const int items = s_bend[nb];                                   // one item = one edge pixel, both rays
     int b = 0;
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
         while (it >= s_bend[b + 1]) b++;                             // `it` only grows: b is monotone
-        const uint2 e = __ldg(elist + s_boff[b] + ((it - s_bend[b]) >> 1));
+        const uint2 e = __ldg(elist + s_boff[b] + (it - s_bend[b]));
         const int x = e.x & 0xffff, y = e.x >> 16;
         if (x < rx0 || x > rx1 || y < ry0 || y > ry1) continue;
-        int sx = (int)(short)(e.y & 0xffff), sy = (int)e.y >> 16;
+        const int sx = (int)(short)(e.y & 0xffff), sy = (int)e.y >> 16;
         if (sx == 0 && sy == 0) continue;
-        if (it & 1) { sx = -sx; sy = -sy; }
-        // radii whose cell lies in [X0,X1] x [Y0,Y1]  (float, conservative by < 1 step each side)
-        float lo = 1.0f, hi = (float)MAX_R;
+        // Signed radii t (cell = pixel + t * step, t in [-30,-1] U [1,30]) whose cell lies in
+        // [X0,X1] x [Y0,Y1]: one interval [lo,hi] in float, conservative by < 1 step each side.
+        float lo = -(float)MAX_R, hi = (float)MAX_R;
         if (sx != 0) {
             float inv = __fdividef(1024.0f, (float)sx);
             float ta = (float)(X0 - x) * inv, tb = (float)(X1 + 1 - x) * inv;
@@ -195,10 +205,22 @@ __global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks(const uint2 *__rest
             lo = fmaxf(lo, fminf(ta, tb)); hi = fminf(hi, fmaxf(ta, tb));
         } else if (y < Y0 || y > Y1) continue;
         // 0.25 of slack covers the error of the approximate divide; at most one extra step per side
-        const int r_lo = max(MIN_R, (int)floorf(lo - 0.25f)), r_hi = min(MAX_R, (int)ceilf(hi + 0.25f));
-        int x1 = (x - cx0) * 1024 + r_lo * sx, y1 = (y - cy0) * 1024 + r_lo * sy;
-        for (int r = r_lo; r <= r_hi; r++, x1 += sx, y1 += sy)
-            atomicAdd(s_acc + (y1 >> 10) * AP + (x1 >> 10), 1);
+        const int t_lo = max(-MAX_R, (int)floorf(lo - 0.25f)), t_hi = min(MAX_R, (int)ceilf(hi + 0.25f));
+        const int xb = (x - cx0) * 1024, yb = (y - cy0) * 1024;
+        {   // forward ray: t = max(t_lo,1) .. t_hi
+            const int r0 = max(t_lo, MIN_R);
+            int x1 = xb + r0 * sx, y1 = yb + r0 * sy;
+#pragma unroll 4
+            for (int r = r0; r <= t_hi; r++, x1 += sx, y1 += sy)
+                atomicAdd(s_acc + (y1 >> 10) * AP + (x1 >> 10), 1);
+        }
+        {   // backward ray: t = -1 down to t_lo, i.e. radius r = -t
+            const int r0 = max(-t_hi, MIN_R), r1 = -t_lo;
+            int x1 = xb - r0 * sx, y1 = yb - r0 * sy;
+#pragma unroll 4
+            for (int r = r0; r <= r1; r++, x1 -= sx, y1 -= sy)
+                atomicAdd(s_acc + (y1 >> 10) * AP + (x1 >> 10), 1);
+        }
     }
     __syncthreads();
     // cells outside the image never receive votes in the reference: clear what the conservative
