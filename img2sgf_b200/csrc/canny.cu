@@ -8,6 +8,7 @@
 #include "canny.cuh"
 #include "profile.cuh"
 #include "tma.cuh"
+#include "roll_cores.cuh"
 
 namespace i2s {
 
@@ -144,6 +145,122 @@ __global__ void __launch_bounds__(256) k_sobel_nms(const MapSet ms, uint8_t *__r
         if (al && x + 3 < w) *reinterpret_cast<uint32_t *>(state + o) = packed;
         else
             for (int k = 0; k < 4 && x + k < w; k++) state[o + k] = (uint8_t)(packed >> (8 * k));
+    }
+}
+
+// ------------------------------------------------------------------ Sobel + NMS, register rolling
+// One warp walks down a strip of 128 loaded / 120 stored columns; each lane owns one word (4 pixels)
+// per row.  Rolling state per lane: three pixel rows as shifted pairs + horizontal smoothing, three
+// magnitude rows with their shifted pairs, two gradient rows.  Per row: one coalesced load (three
+// for RGB), two shuffles of the raw words, the packed Sobel/L1 magnitude (two pixels per
+// instruction), two shuffles of the magnitudes and the branch-free packed NMS of the row two
+// above (roll_cores.cuh).  The diagonal-sector test runs only when some lane of the warp has a
+// diagonal candidate.  No shared memory, no barriers.
+constexpr int CR_TH = 64, CR_OW = 120, CR_WARPS = 8;
+
+template <int CH>
+__device__ __forceinline__ void canny_load(const uint8_t *__restrict__ row, int x, int w, bool al, uint32_t (&ch)[CH])
+{
+    if (CH == 1) {
+        if (al && x >= 0 && x + 3 < w) { ch[0] = __ldg(reinterpret_cast<const uint32_t *>(row + x)); return; }
+        if (x >= w + 8 || x < -8) { ch[0] = 0; return; }
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) v |= (uint32_t)__ldg(row + min(max(x + k, 0), w - 1)) << (8 * k);
+        ch[0] = v;
+    } else {
+        if (al && x >= 0 && x + 3 < w) {
+            const uint32_t *p = reinterpret_cast<const uint32_t *>(row + (size_t)x * 3);
+            const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+            ch[0] = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);
+            ch[1 % CH] = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);
+            ch[2 % CH] = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);
+            return;
+        }
+#pragma unroll
+        for (int c = 0; c < CH; c++) ch[c] = 0;
+        if (x >= w + 8 || x < -8) return;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint8_t *p = row + (size_t)min(max(x + k, 0), w - 1) * CH;
+#pragma unroll
+            for (int c = 0; c < CH; c++) ch[c] |= (uint32_t)__ldg(p + c) << (8 * k);
+        }
+    }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(CR_WARPS * 32) k_canny_roll(const MapSet ms, uint8_t *__restrict__ state, int h, int w,
+                                                              uint32_t low1, uint32_t high1, bool al, int strips_x,
+                                                              int strips_y, int total)
+{
+    const int lane = threadIdx.x & 31;
+    const int strip = blockIdx.x * CR_WARPS + (threadIdx.x >> 5);
+    if (strip >= total) return;                                // warp-uniform
+    const int sx = strip % strips_x, t = strip / strips_x, sy = t % strips_y, map = t / strips_y;
+    const size_t plane = (size_t)h * w;
+    const uint8_t *img = ms.plane(map, plane * CH);
+    uint8_t *out = state + map * plane;
+    const int x = sx * CR_OW - 4 + 4 * lane;
+    const int y0 = sy * CR_TH, y1 = min(y0 + CR_TH, h);
+    const bool store_lane = lane >= 1 && lane <= 30 && x < w;
+    // magnitude is zero outside the image: per-half column masks of this lane's 4 pixels
+    const uint32_t cmA = ((x >= 0 && x < w) ? 0xffffu : 0u) | ((x + 1 >= 0 && x + 1 < w) ? 0xffff0000u : 0u);
+    const uint32_t cmB = ((x + 2 >= 0 && x + 2 < w) ? 0xffffu : 0u) | ((x + 3 >= 0 && x + 3 < w) ? 0xffff0000u : 0u);
+    roll::SobelRow R[3][CH];
+    roll::MagRow M[3];
+    roll::Grad G[2];
+    const int iters = (y1 - y0) + 4;
+#pragma unroll 1
+    for (int ib = 0; ib < iters; ib += 6) {
+#pragma unroll
+        for (int u = 0; u < 6; u++) {
+            const int it = ib + u;
+            if (it < iters) {                                  // warp-uniform
+                const int py = y0 - 2 + it;                    // pixel row loaded in this iteration
+                {
+                    uint32_t ch[CH];
+                    canny_load<CH>(img + (size_t)min(max(py, 0), h - 1) * w * CH, x, w, al, ch);
+#pragma unroll
+                    for (int c = 0; c < CH; c++) {
+                        const uint32_t xl = __shfl_up_sync(0xffffffffu, ch[c], 1) >> 24;
+                        const uint32_t xr = __shfl_down_sync(0xffffffffu, ch[c], 1);
+                        R[u % 3][c] = roll::sobel_row(ch[c], xl, xr);
+                    }
+                }
+                if (it >= 2) {                                 // gradient + magnitude of row gy = py - 1
+                    const int gy = py - 1;
+                    roll::Grad g = roll::sobel_grad(R[(u + 1) % 3][0], R[(u + 2) % 3][0], R[u % 3][0]);
+                    uint32_t mA = g.axA + g.ayA, mB = g.axB + g.ayB;
+#pragma unroll
+                    for (int c = 1; c < CH; c++) {
+                        const roll::Grad gc = roll::sobel_grad(R[(u + 1) % 3][c], R[(u + 2) % 3][c], R[u % 3][c]);
+                        roll::grad_select(g, mA, mB, gc);
+                    }
+                    const bool row_in = gy >= 0 && gy < h;
+                    mA = row_in ? (mA & cmA) : 0u;
+                    mB = row_in ? (mB & cmB) : 0u;
+                    const uint32_t leftB = __shfl_up_sync(0xffffffffu, mB, 1);
+                    const uint32_t rightA = __shfl_down_sync(0xffffffffu, mA, 1);
+                    M[u % 3] = roll::mag_row(mA, mB, leftB, rightA);
+                    G[u % 2] = g;
+                }
+                if (it >= 4) {                                 // NMS of row ny = py - 2
+                    const int ny = py - 2;
+                    const roll::MagRow &up = M[(u + 1) % 3], &c = M[(u + 2) % 3], &dn = M[u % 3];
+                    const roll::Grad &g = G[(u + 1) % 2];
+                    roll::NmsPartial p = roll::nms_axis(up, c, dn, g, low1);
+                    if (__any_sync(0xffffffffu, roll::nms_needs_diag(p, c, low1))) roll::nms_diag(p, up, c, dn, g);
+                    const uint32_t st = roll::nms_state(p, c, high1);
+                    if (store_lane) {
+                        const size_t o = (size_t)ny * w + x;
+                        if (al) *reinterpret_cast<uint32_t *>(out + o) = st;
+                        else
+                            for (int k = 0; k < 4 && x + k < w; k++) out[o + k] = (uint8_t)(st >> (8 * k));
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -289,12 +406,26 @@ int canny_states(const MapSet &ms, int channels, uint8_t *state, int h, int w, i
 {
     const int maps = ms.count * ms.n;
     bool al = (w & 3) == 0 && ((uintptr_t)state & 3) == 0 && ms.aligned4();
-    dim3 g1(cdiv(w, NT), cdiv(h, NT), maps);
     {
     ScopedSection sec(SEC_SOBEL_NMS, st);
-    bool bulk = (w & 15) == 0 && ms.aligned16();
-    if (channels == 1) k_sobel_nms<1><<<g1, 256, 0, st>>>(ms, state, h, w, low, high, al, bulk);
-    else k_sobel_nms<3><<<g1, 256, 0, st>>>(ms, state, h, w, low, high, al, false);
+    if (legacy_enabled("sobel")) {
+        dim3 g1(cdiv(w, NT), cdiv(h, NT), maps);
+        bool bulk = (w & 15) == 0 && ms.aligned16();
+        if (channels == 1) k_sobel_nms<1><<<g1, 256, 0, st>>>(ms, state, h, w, low, high, al, bulk);
+        else k_sobel_nms<3><<<g1, 256, 0, st>>>(ms, state, h, w, low, high, al, false);
+    } else {
+        const int strips_x = cdiv(w, CR_OW), strips_y = cdiv(h, CR_TH);
+        const long long total = (long long)maps * strips_x * strips_y;
+        I2S_ARG(total < (1ll << 31));
+        const unsigned blocks = (unsigned)((total + CR_WARPS - 1) / CR_WARPS);
+        // "m > low" as "m >= low + 1" on 16-bit halves; magnitudes never exceed 2040
+        const uint32_t l1 = (uint32_t)min(max(low + 1, 0), 0xffff), h1 = (uint32_t)min(max(high + 1, 0), 0xffff);
+        const uint32_t low1 = l1 | (l1 << 16), high1 = h1 | (h1 << 16);
+        if (channels == 1)
+            k_canny_roll<1><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total);
+        else
+            k_canny_roll<3><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total);
+    }
     I2S_CHECK_LAUNCH("k_sobel_nms");
     }
     return hysteresis(state, maps, ms.n, h, w, passes, status, scratch, st);

@@ -248,6 +248,141 @@ __global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks(const uint2 *__rest
     }
 }
 
+// ---- second generation of the same kernel -------------------------------------------------------
+// Same tile, same clipping, same atomics; what changed is how the work reaches the lanes:
+//  * the edge-list buckets are walked in groups of 32 items, group g -> warp g % 16, so a warp reads
+//    32 consecutive list entries with one coalesced load and the bucket lookup happens once per group;
+//  * items that cannot reach the tile are dropped BEFORE the vote loops by an order-preserving warp
+//    compaction (ballot + 64-entry ring in shared memory): the loops always run with 32 live rays
+//    whose neighbours in the list are neighbours on the contour, i.e. similar lengths and
+//    conflict-free banks;
+//  * the peak scan reads rows with lane-consecutive columns and tests the threshold first.
+constexpr int VRING = 64;
+constexpr int VOTE2_THREADS = 1024;            // 2 blocks per SM: 64 resident warps
+
+__device__ __forceinline__ void vote_item(int *s_acc, uint2 e, int cx0, int cy0, int X0, int X1, int Y0, int Y1)
+{
+    const int x = e.x & 0xffff, y = e.x >> 16;
+    const int sx = (int)(short)(e.y & 0xffff), sy = (int)e.y >> 16;
+    float lo = -(float)MAX_R, hi = (float)MAX_R;
+    if (sx != 0) {
+        float inv = __fdividef(1024.0f, (float)sx);
+        float ta = (float)(X0 - x) * inv, tb = (float)(X1 + 1 - x) * inv;
+        lo = fmaxf(lo, fminf(ta, tb)); hi = fminf(hi, fmaxf(ta, tb));
+    } else if (x < X0 || x > X1) return;
+    if (sy != 0) {
+        float inv = __fdividef(1024.0f, (float)sy);
+        float ta = (float)(Y0 - y) * inv, tb = (float)(Y1 + 1 - y) * inv;
+        lo = fmaxf(lo, fminf(ta, tb)); hi = fminf(hi, fmaxf(ta, tb));
+    } else if (y < Y0 || y > Y1) return;
+    const int t_lo = max(-MAX_R, (int)floorf(lo - 0.25f)), t_hi = min(MAX_R, (int)ceilf(hi + 0.25f));
+    const int xb = (x - cx0) * 1024, yb = (y - cy0) * 1024;
+    {
+        const int r0 = max(t_lo, MIN_R);
+        int x1 = xb + r0 * sx, y1 = yb + r0 * sy;
+#pragma unroll 4
+        for (int r = r0; r <= t_hi; r++, x1 += sx, y1 += sy) atomicAdd(s_acc + (y1 >> 10) * AP + (x1 >> 10), 1);
+    }
+    {
+        const int r0 = max(-t_hi, MIN_R), r1 = -t_lo;
+        int x1 = xb - r0 * sx, y1 = yb - r0 * sy;
+#pragma unroll 4
+        for (int r = r0; r <= r1; r++, x1 -= sx, y1 -= sy) atomicAdd(s_acc + (y1 >> 10) * AP + (x1 >> 10), 1);
+    }
+}
+
+__global__ void __launch_bounds__(VOTE2_THREADS, 2) k_vote_peaks2(const uint2 *__restrict__ edges,
+                                                              const int2 *__restrict__ dir, int nbx, int nby, int h,
+                                                              int w, int32_t *cand, int32_t *ncand, int cand_cap)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    int *s_acc = reinterpret_cast<int *>(s_raw);                       // AS x AP
+    __shared__ int s_boff[VB * VB], s_gend[VB * VB + 1], s_bcnt[VB * VB];
+    __shared__ uint2 s_ring[VOTE2_THREADS / 32][VRING];
+    const size_t plane = (size_t)h * w;
+    const int map = blockIdx.z;
+    const uint2 *elist = edges + map * plane;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx0 = blockIdx.x * AT, ty0 = blockIdx.y * AT;
+    const int cx0 = tx0 - 1 - AG, cy0 = ty0 - 1 - AG;
+    const int X0 = max(tx0 - 1, 0), X1 = min(tx0 + AT, w - 1);
+    const int Y0 = max(ty0 - 1, 0), Y1 = min(ty0 + AT, h - 1);
+    const int rx0 = max(tx0 - 1 - MAX_R, 0), rx1 = min(tx0 + AT + MAX_R, w - 1);
+    const int ry0 = max(ty0 - 1 - MAX_R, 0), ry1 = min(ty0 + AT + MAX_R, h - 1);
+    const int bx0 = rx0 / EB, bx1 = rx1 / EB, by0 = ry0 / EB, by1 = ry1 / EB;
+    const int nbw = bx1 - bx0 + 1, nb = nbw * (by1 - by0 + 1);      // <= VB*VB
+    for (int i = threadIdx.x; i < AS * AP; i += blockDim.x) s_acc[i] = 0;
+    if (threadIdx.x < nb) {
+        const int b = threadIdx.x;
+        const int2 d = dir[((size_t)map * nby + by0 + b / nbw) * nbx + bx0 + b % nbw];
+        s_boff[b] = d.x;
+        s_bcnt[b] = d.y;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        s_gend[0] = 0;
+        for (int b = 0; b < nb; b++) { run += (s_bcnt[b] + 31) >> 5; s_gend[b + 1] = run; }
+    }
+    __syncthreads();
+    const int groups = s_gend[nb];
+    uint2 *ring = s_ring[warp];
+    const uint32_t lt = (1u << lane) - 1u;
+    int head = 0, pending = 0;                                      // ring write position / live entries (warp-uniform)
+    int b = 0;
+    for (int g = warp; g < groups; g += VOTE2_THREADS / 32) {
+        while (g >= s_gend[b + 1]) b++;                              // g only grows: b is monotone
+        const int i = (g - s_gend[b]) * 32 + lane;
+        bool ok = i < s_bcnt[b];
+        uint2 e = make_uint2(0, 0);
+        if (ok) {
+            e = __ldg(elist + s_boff[b] + i);
+            const int x = e.x & 0xffff, y = e.x >> 16;
+            ok = e.y != 0 && x >= rx0 && x <= rx1 && y >= ry0 && y <= ry1;
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+        if (ok) ring[(head + __popc(m & lt)) & (VRING - 1)] = e;
+        const int cnt = __popc(m);
+        head += cnt; pending += cnt;
+        __syncwarp();
+        if (pending >= 32) {
+            const uint2 it = ring[(head - pending + lane) & (VRING - 1)];
+            pending -= 32;
+            __syncwarp();
+            vote_item(s_acc, it, cx0, cy0, X0, X1, Y0, Y1);
+        }
+    }
+    if (lane < pending) vote_item(s_acc, ring[(head - pending + lane) & (VRING - 1)], cx0, cy0, X0, X1, Y0, Y1);
+    __syncthreads();
+    if (cx0 < 0 || cy0 < 0 || cx0 + AS > w || cy0 + AS > h) {
+        for (int i = threadIdx.x; i < AS * AS; i += blockDim.x) {
+            int ly = i / AS, lx = i - ly * AS;
+            int cx = cx0 + lx, cy = cy0 + ly;
+            if (cx < 0 || cy < 0 || cx >= w || cy >= h) s_acc[ly * AP + lx] = 0;
+        }
+        __syncthreads();
+    }
+    // K6: 4-neighbour peaks above the accumulator threshold, interior cells only (x,y >= 1)
+    const int aw = w + 2;
+    for (int ty = warp; ty < AT; ty += VOTE2_THREADS / 32) {
+        const int cy = ty0 + ty;
+        if (cy < 1 || cy >= h) continue;                             // warp-uniform
+        const int *row = s_acc + (ty + 1 + AG) * AP + 1 + AG;
+#pragma unroll
+        for (int j = 0; j < AT / 32; j++) {
+            const int tx = lane + 32 * j, cx = tx0 + tx;
+            const int v = row[tx];
+            if (v > ACC_THR && cx >= 1 && cx < w) {
+                const int *c = row + tx;
+                if (v > c[-1] && v >= c[1] && v > c[-AP] && v >= c[AP]) {
+                    int slot = atomicAdd(ncand + map, 1);
+                    if (slot < cand_cap) cand[(size_t)map * cand_cap + slot] = cy * aw + cx;
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ K7a: radius estimation
 // One warp per candidate centre.  Only pixels within 30 px can contribute, so the warp scans
 // the 60x60 window of the edge map around the centre instead of the whole non-zero list.
@@ -583,9 +718,11 @@ int hough_circles_maps(const MapSet &ms, int h, int w, float *mcirc, int32_t *mc
     }
     {
         ScopedSection sec(SEC_VOTE, st);
-        I2S_CUDA(cudaFuncSetAttribute(k_vote_peaks, cudaFuncAttributeMaxDynamicSharedMemorySize, VOTE_SMEM));
-        k_vote_peaks<<<dim3(cdiv(w, AT), cdiv(h, AT), maps), VOTE_THREADS, VOTE_SMEM, st>>>(edges, dir, nbx, nby, h, w,
-                                                                                           cand, ncand, lim.cand_cap);
+        const bool legacy = legacy_enabled("vote");
+        auto kern = legacy ? k_vote_peaks : k_vote_peaks2;
+        I2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, VOTE_SMEM));
+        kern<<<dim3(cdiv(w, AT), cdiv(h, AT), maps), legacy ? VOTE_THREADS : VOTE2_THREADS, VOTE_SMEM, st>>>(
+            edges, dir, nbx, nby, h, w, cand, ncand, lim.cand_cap);
         I2S_CHECK_LAUNCH("k_vote_peaks");
     }
     {

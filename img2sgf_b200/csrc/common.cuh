@@ -9,6 +9,7 @@ namespace i2s {
 
 void set_error(const char *fmt, ...);
 void count_launch();
+bool legacy_enabled(const char *name);
 
 #define I2S_CHECK_LAUNCH(what)                                              \
     do {                                                                    \

@@ -2,9 +2,12 @@
 // Reference call sites: img2sgf.py:142-144 (contrast), :153 (grey), :174 (median), :175 (Gaussian).
 // Arithmetic: SURVEY.md Appendix A.1, A.2, A.3, A.9 (all integer / fixed point, bit-exact).
 #include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "profile.cuh"
 #include "tma.cuh"
+#include "roll_cores.cuh"
 
 namespace i2s {
 
@@ -15,6 +18,17 @@ void set_error(const char *fmt, ...)
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// I2S_LEGACY=name[,name...] selects the previous generation of a kernel (A/B runs on the GPU box).
+bool legacy_enabled(const char *name)
+{
+    const char *e = getenv("I2S_LEGACY");
+    if (!e) return false;
+    const size_t n = strlen(name);
+    for (const char *p = e; (p = strstr(p, name)) != nullptr; p += n)
+        if ((p == e || p[-1] == ',') && (p[n] == 0 || p[n] == ',')) return true;
+    return false;
 }
 
 // ------------------------------------------------------------------ grey (A.1)
@@ -133,6 +147,89 @@ __global__ void __launch_bounds__(256) k_gauss357(const uint8_t *__restrict__ sr
                 if (d3) d3[o + k] = (uint8_t)(o3 >> (8 * k));
                 if (d5) d5[o + k] = (uint8_t)(o5 >> (8 * k));
                 if (d7) d7[o + k] = (uint8_t)(o7 >> (8 * k));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ Gaussian 3/5/7, register rolling (A.2)
+// One warp walks down a strip of 128 loaded / 120 stored columns: each lane owns one 32-bit word
+// (4 pixels) per row and keeps the last 7 rows as unpacked pairs in registers.  Per row: one
+// coalesced 128-byte load per warp, the three vertical passes on packed 16-bit halves (Q8 sums
+// fit), an exchange of the edge pairs with the neighbour lanes (8 shuffles) and the three
+// horizontal passes as 16-bit x 8-bit dot products (IDP.2A) into Q16, one rounding.  Lanes 0 and
+// 31 only supply the halo.  No shared memory, no barriers; arithmetic in roll_cores.cuh.
+constexpr int GR_TH = 64;          // output rows per warp strip
+constexpr int GR_OW = 120;         // output columns per warp strip
+constexpr int GR_WARPS = 8;
+
+__device__ __forceinline__ uint32_t load_word_border(const uint8_t *__restrict__ row, int x, int w, bool al, int mode)
+{
+    if (al && x >= 0 && x + 3 < w) return __ldg(reinterpret_cast<const uint32_t *>(row + x));
+    if (x >= w + 8 || x < -8) return 0;                       // beyond any halo: value never used
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) v |= (uint32_t)__ldg(row + border_index(x + k, w, mode)) << (8 * k);
+    return v;
+}
+
+__global__ void __launch_bounds__(GR_WARPS * 32) k_gauss357_roll(const uint8_t *__restrict__ src, uint8_t *__restrict__ d3,
+                                                                 uint8_t *__restrict__ d5, uint8_t *__restrict__ d7, int h,
+                                                                 int w, bool al, int strips_x, int strips_y, int total)
+{
+    const int lane = threadIdx.x & 31;
+    const int strip = blockIdx.x * GR_WARPS + (threadIdx.x >> 5);
+    if (strip >= total) return;                                // warp-uniform
+    const int sx = strip % strips_x, t = strip / strips_x, sy = t % strips_y, img = t / strips_y;
+    const size_t plane = (size_t)h * w;
+    const uint8_t *im = src + img * plane;
+    const int x = sx * GR_OW - 4 + 4 * lane;
+    const int y0 = sy * GR_TH, y1 = min(y0 + GR_TH, h);
+    const bool store_lane = lane >= 1 && lane <= 30 && x < w;
+    uint32_t wl[7], wh[7];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const uint32_t v = load_word_border(im + (size_t)border_index(y0 - 3 + k, h, BORDER_REFLECT101) * w, x, w, al,
+                                            BORDER_REFLECT101);
+        wl[k] = roll::pair_lo(v); wh[k] = roll::pair_hi(v);
+    }
+#pragma unroll 1
+    for (int yb = y0; yb < y1; yb += 7) {
+#pragma unroll
+        for (int u = 0; u < 7; u++) {
+            const int y = yb + u;
+            if (y < y1) {                                      // warp-uniform
+                const uint32_t v = load_word_border(im + (size_t)border_index(y + 3, h, BORDER_REFLECT101) * w, x, w,
+                                                    al, BORDER_REFLECT101);
+                wl[(u + 6) % 7] = roll::pair_lo(v); wh[(u + 6) % 7] = roll::pair_hi(v);
+                const uint32_t rl[7] = {wl[u % 7], wl[(u + 1) % 7], wl[(u + 2) % 7], wl[(u + 3) % 7], wl[(u + 4) % 7],
+                                        wl[(u + 5) % 7], wl[(u + 6) % 7]};
+                const uint32_t rh[7] = {wh[u % 7], wh[(u + 1) % 7], wh[(u + 2) % 7], wh[(u + 3) % 7], wh[(u + 4) % 7],
+                                        wh[(u + 5) % 7], wh[(u + 6) % 7]};
+                uint32_t V[6];
+                roll::gauss_vertical(rl, rh, V);
+                // neighbour pairs: left lane's (V2,V3) [and (V0,V1) for the 7-tap], right lane's (V0,V1) [and (V2,V3)]
+                const uint32_t l3 = __shfl_up_sync(0xffffffffu, V[1], 1), r3 = __shfl_down_sync(0xffffffffu, V[0], 1);
+                const uint32_t l5 = __shfl_up_sync(0xffffffffu, V[3], 1), r5 = __shfl_down_sync(0xffffffffu, V[2], 1);
+                const uint32_t l7 = __shfl_up_sync(0xffffffffu, V[5], 1), r7 = __shfl_down_sync(0xffffffffu, V[4], 1);
+                const uint32_t ll7 = __shfl_up_sync(0xffffffffu, V[4], 1), rr7 = __shfl_down_sync(0xffffffffu, V[5], 1);
+                if (store_lane) {
+                    const uint32_t o3 = roll::gauss_h3(l3, V[0], V[1], r3);
+                    const uint32_t o5 = roll::gauss_h5(l5, V[2], V[3], r5);
+                    const uint32_t o7 = roll::gauss_h7(ll7, l7, V[4], V[5], r7, rr7);
+                    const size_t o = img * plane + (size_t)y * w + x;
+                    if (al) {
+                        if (d3) *reinterpret_cast<uint32_t *>(d3 + o) = o3;
+                        if (d5) *reinterpret_cast<uint32_t *>(d5 + o) = o5;
+                        if (d7) *reinterpret_cast<uint32_t *>(d7 + o) = o7;
+                    } else {
+                        for (int k = 0; k < 4 && x + k < w; k++) {
+                            if (d3) d3[o + k] = (uint8_t)(o3 >> (8 * k));
+                            if (d5) d5[o + k] = (uint8_t)(o5 >> (8 * k));
+                            if (d7) d7[o + k] = (uint8_t)(o7 >> (8 * k));
+                        }
+                    }
+                }
             }
         }
     }
@@ -394,10 +491,18 @@ extern "C" int i2s_gauss357(const uint8_t *src, uint8_t *dst3, uint8_t *dst5, ui
     I2S_ARG(src && n >= 0 && h > 0 && w > 0);
     if (n == 0) return I2S_OK;
     bool al = (w & 3) == 0 && (((uintptr_t)src | (uintptr_t)dst3 | (uintptr_t)dst5 | (uintptr_t)dst7) & 3) == 0;
-    dim3 grid(cdiv(w, GT_W), cdiv(h, GT_H), n);
     ScopedSection sec(SEC_GAUSS, (cudaStream_t)stream);
-    bool bulk = (w & 15) == 0 && ((uintptr_t)src & 15) == 0;
-    k_gauss357<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst3, dst5, dst7, h, w, al, bulk);
+    if (legacy_enabled("gauss")) {
+        dim3 grid(cdiv(w, GT_W), cdiv(h, GT_H), n);
+        bool bulk = (w & 15) == 0 && ((uintptr_t)src & 15) == 0;
+        k_gauss357<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst3, dst5, dst7, h, w, al, bulk);
+    } else {
+        const int strips_x = cdiv(w, GR_OW), strips_y = cdiv(h, GR_TH);
+        const long long total = (long long)n * strips_x * strips_y;
+        I2S_ARG(total < (1ll << 31));
+        k_gauss357_roll<<<(unsigned)((total + GR_WARPS - 1) / GR_WARPS), GR_WARPS * 32, 0, (cudaStream_t)stream>>>(
+            src, dst3, dst5, dst7, h, w, al, strips_x, strips_y, (int)total);
+    }
     I2S_CHECK_LAUNCH("k_gauss357");
     return I2S_OK;
 }
