@@ -5,7 +5,7 @@
 // Everything here is exact integer arithmetic.
 //
 // The functions are host+device so that tests/host/roll_host.cpp can run the very same code
-// lane by lane on the CPU (no GPU in the build container) and compare it with the oracle.
+// lane by lane on the CPU (no GPU in the build container) and compare it with the CPU checker.
 #pragma once
 #include <stdint.h>
 
