@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) k_sobel_nms(const MapSet ms, uint8_t *__r
 // instruction), two shuffles of the magnitudes and the branch-free packed NMS of the row two
 // above (roll_cores.cuh).  The diagonal-sector test runs only when some lane of the warp has a
 // diagonal candidate.  No shared memory, no barriers.
-constexpr int CR_TH = 64, CR_OW = 120, CR_WARPS = 8;
+constexpr int CR_TH = 64, CR_OW = 120, CR_WARPS = 4;
 
 template <int CH>
 __device__ __forceinline__ void canny_load(const uint8_t *__restrict__ row, int x, int w, bool al, uint32_t (&ch)[CH])
@@ -189,8 +189,8 @@ __device__ __forceinline__ void canny_load(const uint8_t *__restrict__ row, int 
     }
 }
 
-template <int CH>
-__global__ void __launch_bounds__(CR_WARPS * 32) k_canny_roll(const MapSet ms, uint8_t *__restrict__ state, int h, int w,
+template <int CH, int MINB>
+__global__ void __launch_bounds__(CR_WARPS * 32, MINB) k_canny_roll(const MapSet ms, uint8_t *__restrict__ state, int h, int w,
                                                               uint32_t low1, uint32_t high1, bool al, int strips_x,
                                                               int strips_y, int total)
 {
@@ -211,16 +211,20 @@ __global__ void __launch_bounds__(CR_WARPS * 32) k_canny_roll(const MapSet ms, u
     roll::MagRow M[3];
     roll::Grad G[2];
     const int iters = (y1 - y0) + 4;
+    uint32_t nxt[CH];                                          // row loaded one iteration ahead of its use
+    canny_load<CH>(img + (size_t)min(max(y0 - 2, 0), h - 1) * w * CH, x, w, al, nxt);
 #pragma unroll 1
     for (int ib = 0; ib < iters; ib += 6) {
 #pragma unroll
         for (int u = 0; u < 6; u++) {
             const int it = ib + u;
             if (it < iters) {                                  // warp-uniform
-                const int py = y0 - 2 + it;                    // pixel row loaded in this iteration
+                const int py = y0 - 2 + it;                    // pixel row consumed in this iteration
                 {
                     uint32_t ch[CH];
-                    canny_load<CH>(img + (size_t)min(max(py, 0), h - 1) * w * CH, x, w, al, ch);
+#pragma unroll
+                    for (int c = 0; c < CH; c++) ch[c] = nxt[c];
+                    canny_load<CH>(img + (size_t)min(max(py + 1, 0), h - 1) * w * CH, x, w, al, nxt);
 #pragma unroll
                     for (int c = 0; c < CH; c++) {
                         const uint32_t xl = __shfl_up_sync(0xffffffffu, ch[c], 1) >> 24;
@@ -271,17 +275,19 @@ __global__ void __launch_bounds__(CR_WARPS * 32) k_canny_roll(const MapSet ms, u
 // queue never exceeds the staged area.  A tile whose outermost interior ring changed marks
 // its 8 neighbours dirty for the next pass; passes repeat until no tile is dirty.
 constexpr int HT = 128;
-constexpr int HS_W = HT + 8, HS_H = HT + 2;      // staged: x halo 4 (aligned), y halo 1
+constexpr int HX = 16;                            // staged x halo: rows are 16-byte aligned bulk copies
+constexpr int HS_W = HT + 2 * HX, HS_H = HT + 2;  // y halo 1
 constexpr int HQ = (HT + 2) * (HT + 2);
 
 __global__ void __launch_bounds__(256) k_hysteresis(uint8_t *__restrict__ state, int h, int w, int tiles_x,
                                                     int tiles_y, uint8_t *dirty_in, uint8_t *dirty_out,
-                                                    int pass, bool al)
+                                                    int pass, bool al, bool bulk)
 {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     uint8_t *s_map = s_dyn;                                              // HS_H * HS_W bytes
     uint16_t *s_q = reinterpret_cast<uint16_t *>(s_dyn + HS_H * HS_W);   // HQ entries
     __shared__ int s_qn, s_changed, s_ring;
+    __shared__ uint64_t s_bar;
     const int tile = (blockIdx.z * tiles_y + blockIdx.y) * tiles_x + blockIdx.x;
     if (pass > 0) {
         const int d = dirty_in[tile];
@@ -293,12 +299,35 @@ __global__ void __launch_bounds__(256) k_hysteresis(uint8_t *__restrict__ state,
     uint8_t *img = state + blockIdx.z * plane;
     const int x0 = blockIdx.x * HT, y0 = blockIdx.y * HT;
     if (threadIdx.x == 0) { s_qn = 0; s_changed = 0; s_ring = 0; }
-    stage_tile_u8(s_map, HS_W, img, h, w, x0 - 4, y0 - 1, HS_W, HS_H, BORDER_ZERO, al);
+    if (bulk) {
+        // in-image part of every staged row with one bulk copy per row; the rest (tiles on the image
+        // border only) is zero-filled with ordinary stores to bytes the copies do not touch
+        const int cxa = max(x0 - HX, 0), cxb = min(x0 + HT + HX, w);
+        const int ra = max(0, 1 - y0), rb = min(HS_H, h - y0 + 1);          // staged rows [ra, rb) lie in the image
+        const int off = cxa - (x0 - HX);
+        if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            if (threadIdx.x == 0) mbar_arrive_expect_tx(&s_bar, (uint32_t)((rb - ra) * (cxb - cxa)));
+            for (int r = ra + threadIdx.x; r < rb; r += 32)
+                bulk_g2s(s_map + r * HS_W + off, img + (size_t)(y0 - 1 + r) * w + cxa, (uint32_t)(cxb - cxa), &s_bar);
+        }
+        if (ra > 0 || rb < HS_H || off > 0 || cxb - (x0 - HX) < HS_W) {
+            const int wa = off >> 2, wb = (cxb - (x0 - HX)) >> 2;           // staged words [wa, wb) are copied
+            for (int idx = threadIdx.x; idx < HS_H * (HS_W / 4); idx += blockDim.x) {
+                const int r = idx / (HS_W / 4), c = idx - r * (HS_W / 4);
+                if (r < ra || r >= rb || c < wa || c >= wb) reinterpret_cast<uint32_t *>(s_map)[idx] = 0u;
+            }
+        }
+        mbar_wait(&s_bar, 0);
+    } else {
+        stage_tile_u8(s_map, HS_W, img, h, w, x0 - HX, y0 - 1, HS_W, HS_H, BORDER_ZERO, al);
+    }
     __syncthreads();
     // seeds: interior candidates that already touch an edge pixel (of the tile or of the ring).  Scanning
     // from the weak side keeps the queue tiny: most edge pixels have no weak neighbour at all.
     for (int idx = threadIdx.x; idx < HT * (HT / 4); idx += blockDim.x) {
-        const int ly = idx / (HT / 4) + 1, wx = idx % (HT / 4) + 1;          // staged word wx holds lx = 4wx-3 .. 4wx
+        const int ly = idx / (HT / 4) + 1, wx = idx % (HT / 4) + HX / 4;     // staged word wx holds lx = 4wx-(HX-1) ..
         const uint32_t v = *reinterpret_cast<const uint32_t *>(s_map + ly * HS_W + 4 * wx);
         uint32_t weak = v & ~(v >> 1) & 0x01010101u;                         // bit0 set, bit1 clear: weak candidate
         while (weak) {
@@ -312,7 +341,7 @@ __global__ void __launch_bounds__(256) k_hysteresis(uint8_t *__restrict__ state,
             const int sh = 8 * (b & 3);
             const uint32_t old = atomicOr(word, 2u << sh);
             if (((old >> sh) & 3u) == 1u) {
-                const int lx = 4 * wx + k - 3;
+                const int lx = 4 * wx + k - (HX - 1);
                 s_q[atomicAdd(&s_qn, 1)] = (uint16_t)(ly * (HT + 2) + lx);
                 s_changed = 1;
                 if (ly == 1 || ly == HT || lx == 1 || lx == HT) s_ring = 1;
@@ -335,7 +364,7 @@ __global__ void __launch_bounds__(256) k_hysteresis(uint8_t *__restrict__ state,
                     if (dx == 0 && dy == 0) continue;
                     int ny = ly + dy, nx = lx + dx;
                     if (ny < 1 || ny > HT || nx < 1 || nx > HT) continue;   // promote interior only
-                    int b = ny * HS_W + nx + 3;
+                    int b = ny * HS_W + nx + HX - 1;
                     if ((s_map[b] & 3) != 1) continue;
                     uint32_t *word = reinterpret_cast<uint32_t *>(s_map + (b & ~3));
                     int sh = 8 * (b & 3);
@@ -354,7 +383,7 @@ __global__ void __launch_bounds__(256) k_hysteresis(uint8_t *__restrict__ state,
         int ty = idx / (HT / 4), gx = (idx - ty * (HT / 4)) * 4;
         int y = y0 + ty, x = x0 + gx;
         if (y >= h || x >= w) continue;
-        uint32_t v = *reinterpret_cast<const uint32_t *>(s_map + (ty + 1) * HS_W + gx + 4);
+        uint32_t v = *reinterpret_cast<const uint32_t *>(s_map + (ty + 1) * HS_W + gx + HX);
         size_t o = (size_t)y * w + x;
         if (al && x + 3 < w) *reinterpret_cast<uint32_t *>(img + o) = v;
         else
@@ -421,10 +450,15 @@ int canny_states(const MapSet &ms, int channels, uint8_t *state, int h, int w, i
         // "m > low" as "m >= low + 1" on 16-bit halves; magnitudes never exceed 2040
         const uint32_t l1 = (uint32_t)min(max(low + 1, 0), 0xffff), h1 = (uint32_t)min(max(high + 1, 0), 0xffff);
         const uint32_t low1 = l1 | (l1 << 16), high1 = h1 | (h1 << 16);
-        if (channels == 1)
-            k_canny_roll<1><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total);
-        else
-            k_canny_roll<3><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total);
+        if (channels == 1) {
+            // 6 resident blocks (80 registers, a few spilled words) against 5 (100 registers): A/B switch
+            if (legacy_enabled("canny5"))
+                k_canny_roll<1, 5><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total);
+            else
+                k_canny_roll<1, 6><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total);
+        } else {
+            k_canny_roll<3, 4><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total);
+        }
     }
     I2S_CHECK_LAUNCH("k_sobel_nms");
     }
@@ -435,6 +469,7 @@ int hysteresis(uint8_t *state, int maps, int n_images, int h, int w, int passes,
                void *scratch, cudaStream_t st)
 {
     bool al = (w & 3) == 0 && ((uintptr_t)state & 3) == 0;
+    bool bulk = (w & 15) == 0 && ((uintptr_t)state & 15) == 0 && !legacy_enabled("hyst");
     ScopedSection sec(SEC_HYSTERESIS, st);
     int tx = cdiv(w, HT), ty = cdiv(h, HT);
     size_t tiles = (size_t)maps * tx * ty;
@@ -450,7 +485,7 @@ int hysteresis(uint8_t *state, int maps, int n_images, int h, int w, int passes,
     }
     for (int p = 0; p < passes; p++) {
         uint8_t *din = (p & 1) ? d1 : d0, *dout = (p & 1) ? d0 : d1;
-        k_hysteresis<<<g, 256, kSmem, st>>>(state, h, w, tx, ty, din, dout, p, al);
+        k_hysteresis<<<g, 256, kSmem, st>>>(state, h, w, tx, ty, din, dout, p, al, bulk);
         I2S_CHECK_LAUNCH("k_hysteresis");
     }
     uint8_t *last = (passes & 1) ? d1 : d0;   // buffer written by the final pass

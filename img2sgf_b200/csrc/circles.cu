@@ -35,6 +35,54 @@ __device__ __forceinline__ void sobel_at(const uint8_t *__restrict__ img, int h,
     dy = (p20 + 2 * p21 + p22) - (p00 + 2 * p01 + p02);
 }
 
+// Second phase shared by both compaction kernels: reserve a slice of the map's list per bucket,
+// publish the directory entry, then recompute the Sobel gradient of every compacted edge pixel
+// and store (position, Q10 step).
+__device__ __forceinline__ void edge_emit(const uint8_t *__restrict__ img, int h, int w, int map, size_t plane,
+                                          uint32_t (*s_pos)[EB * EB], int *s_n, int *s_off, int *s_end,
+                                          uint2 *__restrict__ edges, int32_t *ecount, int2 *dir, int nbx, int nby)
+{
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        const int sub = threadIdx.x;
+        const int bxx = blockIdx.x * 2 + (sub & 1), byy = blockIdx.y * 2 + (sub >> 1);
+        const int n = s_n[sub];
+        int off = 0;
+        if (bxx < nbx && byy < nby) {
+            off = n ? atomicAdd(ecount + map, n) : 0;
+            dir[((size_t)map * nby + byy) * nbx + bxx] = make_int2(off, n);
+        }
+        s_off[sub] = off;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_end[0] = 0;
+        for (int k = 0; k < 4; k++) s_end[k + 1] = s_end[k] + s_n[k];
+    }
+    __syncthreads();
+    uint2 *out = edges + (size_t)map * plane;
+    const int total = s_end[4];
+    int sub = 0;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        while (i >= s_end[sub + 1]) sub++;
+        const int li = i - s_end[sub];
+        const uint32_t e = s_pos[sub][li];
+        const int x = e & 0xffff, y = e >> 16;
+        int dx, dy;
+        sobel_at(img, h, w, x, y, dx, dy);
+        int sx = 0, sy = 0;
+        if (dx != 0 || dy != 0) {
+            float vx = (float)dx, vy = (float)dy;
+            float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)));
+            if (!(mag < 1.0f)) {
+                sx = __float2int_rn(__fdiv_rn(__fmul_rn(vx, 1024.0f), mag));
+                sy = __float2int_rn(__fdiv_rn(__fmul_rn(vy, 1024.0f), mag));
+            }
+        }
+        out[s_off[sub] + li] = make_uint2(e, (uint32_t)(sx & 0xffff) | ((uint32_t)sy << 16));   // (0,0) step = no vote
+    }
+}
+
 __global__ void __launch_bounds__(256) k_edge_buckets(const MapSet ms, const uint8_t *__restrict__ state, int h, int w,
                                                       bool al, uint2 *__restrict__ edges, int32_t *ecount, int2 *dir,
                                                       int nbx, int nby)
@@ -89,45 +137,56 @@ __global__ void __launch_bounds__(256) k_edge_buckets(const MapSet ms, const uin
             s_pos[sub][pos++] = ((uint32_t)y << 16) | (uint32_t)(x + k);
         }
     }
+    edge_emit(img, h, w, map, plane, s_pos, s_n, s_off, s_end, edges, ecount, dir, nbx, nby);
+}
+
+// Same result with 16 pixels (one 128-bit load) per thread: thread t owns row t/4 and the 16-pixel
+// column group t%4 of the block's 64x64 pixels, so a warp covers 8 rows of two buckets (lanes with
+// the same bit 1 share a bucket) and needs one 5-bit ballot prefix per 16 pixels instead of one
+// 3-bit prefix per 4.  Requires w % 16 == 0 and a 16-byte aligned state map.
+__global__ void __launch_bounds__(256) k_edge_buckets16(const MapSet ms, const uint8_t *__restrict__ state, int h, int w,
+                                                        uint2 *__restrict__ edges, int32_t *ecount, int2 *dir,
+                                                        int nbx, int nby)
+{
+    __shared__ uint32_t s_pos[4][EB * EB];
+    __shared__ int s_n[4], s_off[4], s_end[5];
+    const size_t plane = (size_t)h * w;
+    const int map = blockIdx.z;
+    const uint8_t *img = ms.plane(map, plane);
+    const uint8_t *stm = state + map * plane;
+    const int lane = threadIdx.x & 31;
+    const int row = threadIdx.x >> 2, cg = threadIdx.x & 3;
+    const int y = blockIdx.y * (2 * EB) + row, x = blockIdx.x * (2 * EB) + cg * 16;
+    const int sub = (row >> 5) * 2 + (cg >> 1);
+    if (threadIdx.x < 4) s_n[threadIdx.x] = 0;
     __syncthreads();
-    if (threadIdx.x < 4) {
-        const int sub = threadIdx.x;
-        const int bxx = blockIdx.x * 2 + (sub & 1), byy = blockIdx.y * 2 + (sub >> 1);
-        const int n = s_n[sub];
-        int off = 0;
-        if (bxx < nbx && byy < nby) {
-            off = n ? atomicAdd(ecount + map, n) : 0;
-            dir[((size_t)map * nby + byy) * nbx + bxx] = make_int2(off, n);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (y < h && x < w) v = __ldg(reinterpret_cast<const uint4 *>(stm + (size_t)y * w + x));
+    uint32_t wd[4] = {v.x & 0x02020202u, v.y & 0x02020202u, v.z & 0x02020202u, v.w & 0x02020202u};
+    const int nbits = __popc(wd[0]) + __popc(wd[1]) + __popc(wd[2]) + __popc(wd[3]);      // 0..16
+    const uint32_t bm = (lane & 2) ? 0xccccccccu : 0x33333333u;                            // lanes of my bucket
+    const uint32_t lt = ((1u << lane) - 1u) & bm;
+    int pre = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const uint32_t b = __ballot_sync(0xffffffffu, (nbits >> k) & 1);
+        pre += __popc(b & lt) << k;
+        tot += __popc(b & bm) << k;
+    }
+    int base = 0;
+    if ((lane == 0 || lane == 2) && tot) base = atomicAdd(&s_n[sub], tot);
+    base = __shfl_sync(0xffffffffu, base, lane & 2);
+    int pos = base + pre;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t m = wd[k];
+        while (m) {
+            const int j = (__ffs(m) - 1) >> 3;
+            m &= m - 1;
+            s_pos[sub][pos++] = ((uint32_t)y << 16) | (uint32_t)(x + 4 * k + j);
         }
-        s_off[sub] = off;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        s_end[0] = 0;
-        for (int k = 0; k < 4; k++) s_end[k + 1] = s_end[k] + s_n[k];
-    }
-    __syncthreads();
-    uint2 *out = edges + (size_t)map * plane;
-    const int total = s_end[4];
-    int sub = 0;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        while (i >= s_end[sub + 1]) sub++;
-        const int li = i - s_end[sub];
-        const uint32_t e = s_pos[sub][li];
-        const int x = e & 0xffff, y = e >> 16;
-        int dx, dy;
-        sobel_at(img, h, w, x, y, dx, dy);
-        int sx = 0, sy = 0;
-        if (dx != 0 || dy != 0) {
-            float vx = (float)dx, vy = (float)dy;
-            float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)));
-            if (!(mag < 1.0f)) {
-                sx = __float2int_rn(__fdiv_rn(__fmul_rn(vx, 1024.0f), mag));
-                sy = __float2int_rn(__fdiv_rn(__fmul_rn(vy, 1024.0f), mag));
-            }
-        }
-        out[s_off[sub] + li] = make_uint2(e, (uint32_t)(sx & 0xffff) | ((uint32_t)sy << 16));   // (0,0) step = no vote
-    }
+    edge_emit(img, h, w, map, plane, s_pos, s_n, s_off, s_end, edges, ecount, dir, nbx, nby);
 }
 
 // ------------------------------------------------------------------ K5+K6: voting fused with peak finding
@@ -249,17 +308,11 @@ __global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks(const uint2 *__rest
 }
 
 // ---- second generation of the same kernel -------------------------------------------------------
-// Same tile, same clipping, same atomics; what changed is how the work reaches the lanes:
-//  * the edge-list buckets are walked in groups of 32 items, group g -> warp g % 16, so a warp reads
-//    32 consecutive list entries with one coalesced load and the bucket lookup happens once per group;
-//  * items that cannot reach the tile are dropped BEFORE the vote loops by an order-preserving warp
-//    compaction (ballot + 64-entry ring in shared memory): the loops always run with 32 live rays
-//    whose neighbours in the list are neighbours on the contour, i.e. similar lengths and
-//    conflict-free banks;
-//  * the peak scan reads rows with lane-consecutive columns and tests the threshold first.
-constexpr int VRING = 64;
-constexpr int VOTE2_THREADS = 1024;            // 2 blocks per SM: 64 resident warps
-
+// Same tile, same clipping, same atomics.  What changed: every warp owns one contiguous slice of the
+// tile's item sequence (lanes interleaved), so the bucket pointer moves by a step or two per
+// iteration after one binary search per warp, consecutive lanes hold consecutive contour pixels
+// (similar ray lengths, neighbouring banks), and the peak scan reads rows with lane-consecutive
+// columns, testing the threshold before anything else.
 __device__ __forceinline__ void vote_item(int *s_acc, uint2 e, int cx0, int cy0, int X0, int X1, int Y0, int Y1)
 {
     const int x = e.x & 0xffff, y = e.x >> 16;
@@ -291,14 +344,14 @@ __device__ __forceinline__ void vote_item(int *s_acc, uint2 e, int cx0, int cy0,
     }
 }
 
-__global__ void __launch_bounds__(VOTE2_THREADS, 2) k_vote_peaks2(const uint2 *__restrict__ edges,
+__global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks2(const uint2 *__restrict__ edges,
                                                               const int2 *__restrict__ dir, int nbx, int nby, int h,
                                                               int w, int32_t *cand, int32_t *ncand, int cand_cap)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     int *s_acc = reinterpret_cast<int *>(s_raw);                       // AS x AP
-    __shared__ int s_boff[VB * VB], s_gend[VB * VB + 1], s_bcnt[VB * VB];
-    __shared__ uint2 s_ring[VOTE2_THREADS / 32][VRING];
+    __shared__ int s_boff[VB * VB], s_bend[VB * VB + 1];               // bucket slice start / running item end
+    constexpr int NW = VOTE_THREADS / 32;
     const size_t plane = (size_t)h * w;
     const int map = blockIdx.z;
     const uint2 *elist = edges + map * plane;
@@ -316,43 +369,36 @@ __global__ void __launch_bounds__(VOTE2_THREADS, 2) k_vote_peaks2(const uint2 *_
         const int b = threadIdx.x;
         const int2 d = dir[((size_t)map * nby + by0 + b / nbw) * nbx + bx0 + b % nbw];
         s_boff[b] = d.x;
-        s_bcnt[b] = d.y;
+        s_bend[b + 1] = d.y;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         int run = 0;
-        s_gend[0] = 0;
-        for (int b = 0; b < nb; b++) { run += (s_bcnt[b] + 31) >> 5; s_gend[b + 1] = run; }
+        s_bend[0] = 0;
+        for (int b = 0; b < nb; b++) { run += s_bend[b + 1]; s_bend[b + 1] = run; }
     }
     __syncthreads();
-    const int groups = s_gend[nb];
-    uint2 *ring = s_ring[warp];
-    const uint32_t lt = (1u << lane) - 1u;
-    int head = 0, pending = 0;                                      // ring write position / live entries (warp-uniform)
-    int b = 0;
-    for (int g = warp; g < groups; g += VOTE2_THREADS / 32) {
-        while (g >= s_gend[b + 1]) b++;                              // g only grows: b is monotone
-        const int i = (g - s_gend[b]) * 32 + lane;
-        bool ok = i < s_bcnt[b];
-        uint2 e = make_uint2(0, 0);
-        if (ok) {
-            e = __ldg(elist + s_boff[b] + i);
-            const int x = e.x & 0xffff, y = e.x >> 16;
-            ok = e.y != 0 && x >= rx0 && x <= rx1 && y >= ry0 && y <= ry1;
+    const int items = s_bend[nb];
+    {
+        const int per = ((items + NW - 1) / NW + 31) & ~31;          // items per warp, whole rounds of 32
+        const int i0 = warp * per, i1 = min(i0 + per, items);
+        int b = 0;
+        if (i0 < i1) {                                               // bucket holding item i0: s_bend[b] <= i0 < s_bend[b+1]
+            int lo = 0, hi = nb - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (s_bend[mid + 1] <= i0) lo = mid + 1; else hi = mid;
+            }
+            b = lo;
         }
-        const uint32_t m = __ballot_sync(0xffffffffu, ok);
-        if (ok) ring[(head + __popc(m & lt)) & (VRING - 1)] = e;
-        const int cnt = __popc(m);
-        head += cnt; pending += cnt;
-        __syncwarp();
-        if (pending >= 32) {
-            const uint2 it = ring[(head - pending + lane) & (VRING - 1)];
-            pending -= 32;
-            __syncwarp();
-            vote_item(s_acc, it, cx0, cy0, X0, X1, Y0, Y1);
+        for (int it = i0 + lane; it < i1; it += 32) {
+            while (it >= s_bend[b + 1]) b++;                         // `it` only grows: b is monotone
+            const uint2 e = __ldg(elist + s_boff[b] + (it - s_bend[b]));
+            const int x = e.x & 0xffff, y = e.x >> 16;
+            if (e.y == 0 || x < rx0 || x > rx1 || y < ry0 || y > ry1) continue;
+            vote_item(s_acc, e, cx0, cy0, X0, X1, Y0, Y1);
         }
     }
-    if (lane < pending) vote_item(s_acc, ring[(head - pending + lane) & (VRING - 1)], cx0, cy0, X0, X1, Y0, Y1);
     __syncthreads();
     if (cx0 < 0 || cy0 < 0 || cx0 + AS > w || cy0 + AS > h) {
         for (int i = threadIdx.x; i < AS * AS; i += blockDim.x) {
@@ -364,7 +410,7 @@ __global__ void __launch_bounds__(VOTE2_THREADS, 2) k_vote_peaks2(const uint2 *_
     }
     // K6: 4-neighbour peaks above the accumulator threshold, interior cells only (x,y >= 1)
     const int aw = w + 2;
-    for (int ty = warp; ty < AT; ty += VOTE2_THREADS / 32) {
+    for (int ty = warp; ty < AT; ty += NW) {
         const int cy = ty0 + ty;
         if (cy < 1 || cy >= h) continue;                             // warp-uniform
         const int *row = s_acc + (ty + 1 + AG) * AP + 1 + AG;
@@ -713,16 +759,19 @@ int hough_circles_maps(const MapSet &ms, int h, int w, float *mcirc, int32_t *mc
     bool al = (w & 3) == 0 && ((uintptr_t)state & 3) == 0;
     {
         ScopedSection sec(SEC_EDGE_LIST, st);
-        k_edge_buckets<<<dim3(cdiv(nbx, 2), cdiv(nby, 2), maps), 256, 0, st>>>(ms, state, h, w, al, edges, ecount, dir, nbx, nby);
+        const dim3 eg(cdiv(nbx, 2), cdiv(nby, 2), maps);
+        if ((w & 15) == 0 && ((uintptr_t)state & 15) == 0 && !legacy_enabled("edges"))
+            k_edge_buckets16<<<eg, 256, 0, st>>>(ms, state, h, w, edges, ecount, dir, nbx, nby);
+        else
+            k_edge_buckets<<<eg, 256, 0, st>>>(ms, state, h, w, al, edges, ecount, dir, nbx, nby);
         I2S_CHECK_LAUNCH("k_edge_buckets");
     }
     {
         ScopedSection sec(SEC_VOTE, st);
-        const bool legacy = legacy_enabled("vote");
-        auto kern = legacy ? k_vote_peaks : k_vote_peaks2;
+        auto kern = legacy_enabled("vote") ? k_vote_peaks : k_vote_peaks2;
         I2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, VOTE_SMEM));
-        kern<<<dim3(cdiv(w, AT), cdiv(h, AT), maps), legacy ? VOTE_THREADS : VOTE2_THREADS, VOTE_SMEM, st>>>(
-            edges, dir, nbx, nby, h, w, cand, ncand, lim.cand_cap);
+        kern<<<dim3(cdiv(w, AT), cdiv(h, AT), maps), VOTE_THREADS, VOTE_SMEM, st>>>(edges, dir, nbx, nby, h, w, cand, ncand,
+                                                                                   lim.cand_cap);
         I2S_CHECK_LAUNCH("k_vote_peaks");
     }
     {

@@ -193,14 +193,17 @@ __global__ void __launch_bounds__(GR_WARPS * 32) k_gauss357_roll(const uint8_t *
                                             BORDER_REFLECT101);
         wl[k] = roll::pair_lo(v); wh[k] = roll::pair_hi(v);
     }
+    // the row entering the window is loaded one iteration ahead of its use
+    uint32_t nxt = load_word_border(im + (size_t)border_index(y0 + 3, h, BORDER_REFLECT101) * w, x, w, al, BORDER_REFLECT101);
 #pragma unroll 1
     for (int yb = y0; yb < y1; yb += 7) {
 #pragma unroll
         for (int u = 0; u < 7; u++) {
             const int y = yb + u;
             if (y < y1) {                                      // warp-uniform
-                const uint32_t v = load_word_border(im + (size_t)border_index(y + 3, h, BORDER_REFLECT101) * w, x, w,
-                                                    al, BORDER_REFLECT101);
+                const uint32_t v = nxt;
+                nxt = load_word_border(im + (size_t)border_index(y + 4, h, BORDER_REFLECT101) * w, x, w, al,
+                                       BORDER_REFLECT101);
                 wl[(u + 6) % 7] = roll::pair_lo(v); wh[(u + 6) % 7] = roll::pair_hi(v);
                 const uint32_t rl[7] = {wl[u % 7], wl[(u + 1) % 7], wl[(u + 2) % 7], wl[(u + 3) % 7], wl[(u + 4) % 7],
                                         wl[(u + 5) % 7], wl[(u + 6) % 7]};
