@@ -452,6 +452,7 @@ __global__ void __launch_bounds__(RW * 32) k_radius(const uint2 *__restrict__ ed
     __shared__ int s_pref[RW][RBINS];
     __shared__ uint32_t s_mask[RW][RBINS / 32];
     __shared__ float s_rtab[RQ];
+    __shared__ uint16_t s_binlut[900];             // histogram bin of squared distance q + 0.5, q = 1..899
     const int map = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint2 *elist = edges + (size_t)map * h * w;
@@ -464,6 +465,14 @@ __global__ void __launch_bounds__(RW * 32) k_radius(const uint2 *__restrict__ ed
     }
     if (blockIdx.x * RW >= n) return;
     for (int q = threadIdx.x; q < RQ; q += blockDim.x) s_rtab[q] = radius_of_q(q);
+    // Centres sit on half-integers and edge pixels on integers, so the float32 squared distance
+    // (cx+.5-px)^2 + (cy+.5-py)^2 is exactly q + 0.5 with q = dx(dx+1) + dy(dy+1) an integer: the
+    // sqrt / rint chain of SURVEY A.5 step 4 is tabulated once per block over the 899 admissible q.
+    for (int q = threadIdx.x; q < 900; q += blockDim.x) {
+        const float dd = __fsqrt_rn((float)q + 0.5f);
+        const int bin = __float2int_rn(__fmul_rn(__fsub_rn(dd, 1.0f), 10.0f));
+        s_binlut[q] = (uint16_t)min(max(bin, 0), NBINS - 1);
+    }
     __syncthreads();
     int *bins = s_bins[warp], *pref = s_pref[warp];
     uint32_t *mask = s_mask[warp];
@@ -474,7 +483,6 @@ __global__ void __launch_bounds__(RW * 32) k_radius(const uint2 *__restrict__ ed
         __syncwarp();
         // histogram of the distances to the edge pixels within 30 px: walk the edge-list buckets
         // that overlap the 60x60 window (at most 3x3 of them)
-        const float fcx = (float)cx + 0.5f, fcy = (float)cy + 0.5f;
         const int xlo = max(cx - 29, 0), xhi = min(cx + 30, w - 1);
         const int ylo = max(cy - 29, 0), yhi = min(cy + 30, h - 1);
         for (int by = ylo / EB; by <= yhi / EB; by++)
@@ -482,16 +490,9 @@ __global__ void __launch_bounds__(RW * 32) k_radius(const uint2 *__restrict__ ed
                 const int2 d = __ldg(mdir + by * nbx + bx);
                 for (int i = lane; i < d.y; i += 32) {
                     const uint32_t e = __ldg(&elist[d.x + i].x);
-                    const int px = e & 0xffff, py = e >> 16;
-                    if (px < xlo || px > xhi || py < ylo || py > yhi) continue;
-                    float ddx = fcx - (float)px, ddy = fcy - (float)py;
-                    float r2 = __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy));
-                    if (r2 >= 1.0f && r2 <= 900.0f) {
-                        float dd = __fsqrt_rn(r2);
-                        int bin = __float2int_rn(__fmul_rn(__fsub_rn(dd, 1.0f), 10.0f));
-                        bin = min(max(bin, 0), NBINS - 1);
-                        atomicAdd(bins + bin, 1);
-                    }
+                    const int dxi = cx - (int)(e & 0xffff), dyi = cy - (int)(e >> 16);
+                    const int q = dxi * dxi + dxi + dyi * dyi + dyi;         // 1 <= r2 <= 900  <=>  1 <= q <= 899
+                    if ((unsigned)(q - 1) < 899u) atomicAdd(bins + s_binlut[q], 1);
                 }
             }
         __syncwarp();

@@ -210,11 +210,15 @@ I2S_HD uint32_t fail_gt_gt(uint32_t m, uint32_t a, uint32_t b) { return max2(max
 // Returns masks (0xffff per half): nh = NOT horizontal, v = vertical.
 I2S_HD void sector_masks(uint32_t ax, uint32_t ay, uint32_t &nh, uint32_t &v)
 {
-    const uint32_t u = prmt(ax * 5u, 0, 0x4341);               // (ax*5) >> 8 per half
-    const uint32_t hp = ((ax * 53u + u) >> 7) & 0x01ff01ffu;
-    const uint32_t q = hp + ax + ax;
-    nh = nz_mask(ay - min2(ay, hp));                           // ay > hp
-    v = nz_mask(ay - min2(ay, q));                             // ay > q
+    // horizontal  <=>  ay <= floor(wq / 128), wq = ax*53 + ((ax*5) >> 8)  <=>  128 * min(ay, 511) <= wq
+    // (wq <= 54080, so an ay above 511 can never be horizontal and the product stays inside 16 bits)
+    const uint32_t wq = ax * 53u + prmt(ax * 5u, 0, 0x4341);
+    const uint32_t a128 = min2(ay, 0x01ff01ffu) * 128u;
+    nh = nz_mask(a128 - min2(a128, wq));                       // 128 ay > wq
+    // vertical  <=>  ay > 2 ax + floor(wq / 128)  <=>  128 (ay - 2 ax) > wq  (ay - 2ax clamped to 0..511)
+    const uint32_t two = ax + ax;
+    const uint32_t z128 = min2(ay - min2(ay, two), 0x01ff01ffu) * 128u;
+    v = nz_mask(z128 - min2(z128, wq | 0x007f007fu));          // 128 z > wq  <=>  128 z > (wq | 127)
 }
 
 // NMS + thresholds for the 4 pixels of a lane.  up/c/dn = magnitude rows y-1, y, y+1; g = gradient
@@ -258,10 +262,10 @@ I2S_HD void nms_diag(NmsPartial &p, const MagRow &up, const MagRow &c, const Mag
 
 I2S_HD uint32_t nms_state(const NmsPartial &p, const MagRow &c, uint32_t high1)
 {
-    const uint32_t passA = min2(p.FA, ONE2) ^ ONE2, passB = min2(p.FB, ONE2) ^ ONE2;             // 1 where kept
-    const uint32_t strongA = passA & (min2(max2(c.A, high1) ^ c.A, ONE2) ^ ONE2);
-    const uint32_t strongB = passB & (min2(max2(c.B, high1) ^ c.B, ONE2) ^ ONE2);
-    const uint32_t stA = passA | (strongA << 1), stB = passB | (strongB << 1);
+    // per half: 0 where rejected, else 3 - 2 * (m <= high)
+    const uint32_t nsA = min2(max2(c.A, high1) ^ c.A, ONE2), nsB = min2(max2(c.B, high1) ^ c.B, ONE2);
+    const uint32_t stA = (0x00030003u - nsA - nsA) & ~nz_mask(p.FA);
+    const uint32_t stB = (0x00030003u - nsB - nsB) & ~nz_mask(p.FB);
     return prmt(stA, stB, 0x6420);
 }
 

@@ -32,3 +32,17 @@ if [ -n "$KREGEX" ]; then
   done
 fi
 du -sh gpurun_out
+# optional 4th argument: extra bench runs with several streams
+if [ -n "$4" ]; then
+  for stn in $4; do
+    timeout 600 python bench.py --per-gpu 512 --steps 2 --warmup 2 --no-cpu-baseline --no-e2e --streams $stn > gpurun_out/bench_${TAG}_st$stn.json 2> gpurun_out/bench_${TAG}_st$stn.err
+    python - <<PY
+import json
+try:
+    d=json.loads([l for l in open('gpurun_out/bench_${TAG}_st$stn.json') if l.startswith('{')][-1])
+    print('streams=$stn', round(d['value']), 'img/s', round(d['ms_per_step'],2), 'ms/step', d['check'])
+except Exception as e:
+    print('streams=$stn failed', e); print(open('gpurun_out/bench_${TAG}_st$stn.err').read()[-600:])
+PY
+  done
+fi
