@@ -251,7 +251,6 @@ def run_ours(args, rank, world, local_rank):
     assert full.shape[0] == total
 
     sampler = ClockSampler(local_rank)
-    nsec = lib.i2s_profile_enable(1)
     lib.i2s_launch_count(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(); torch.cuda.synchronize()
@@ -264,15 +263,30 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize(); barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = int(lib.i2s_launch_count(1))
-    ms = (C.c_double * nsec)(); cnt = (C.c_longlong * nsec)()
-    N.check(lib.i2s_profile_read(ms, cnt, nsec), "i2s_profile_read")
-    lib.i2s_profile_enable(0)
     elapsed_ms = e0.elapsed_time(e1)
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
     value = total * args.steps / (elapsed_ms / 1000.0)
+
+    # ---- per-kernel-group section timers (roofline): the same K steps again on ONE stream with the
+    # library's CUDA-event section timers on, so that a kernel's duration is not stretched by kernels
+    # of another stream sharing the SMs.  (With --streams 1 this pass is identical to the timed one.)
+    prof_runner = runner if args.streams == 1 else B.BatchRunner(size, size, chunk, streams=1)
+    prof_runner.run(dev, thr, 128, records=records)
+    torch.cuda.synchronize()
+    nsec = lib.i2s_profile_enable(1)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(args.steps):
+        prof_runner.run(dev, thr, 128, records=records)
+    p1.record()
+    torch.cuda.synchronize()
+    ms = (C.c_double * nsec)(); cnt = (C.c_longlong * nsec)()
+    N.check(lib.i2s_profile_read(ms, cnt, nsec), "i2s_profile_read")
+    lib.i2s_profile_enable(0)
+    prof_ms_per_step = p0.elapsed_time(p1) / args.steps
 
     # ---- end to end: pinned host RGB in, host records out, every step
     e2e = None
@@ -328,6 +342,14 @@ def run_ours(args, rank, world, local_rank):
         calls_per_step = 8 * per_gpu                     # unique HoughCircles inputs per image (SURVEY Fact 2)
         alg_bytes = 10.0 * size * size * calls_per_step  # 10*P per call: image+edges read, int32 acc store+load
         achieved = alg_bytes / (acc_ms / 1000.0) / 1e9 if acc_ms > 0 else None
+        # DRAM traffic of the two kernels from the committed ncu capture (bytes per HoughCircles call,
+        # scaled to the calls one launch of this run processes); null if the capture is absent
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_hough_accum_traffic.json")))
+            traffic = float(tr["dram_bytes_per_call"]) * 8 * min(chunk, per_gpu)
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
@@ -339,11 +361,16 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "hough_accum (k_edge_buckets + k_vote_peaks: vote + peak find fused), 8 calls/image",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "traffic_note": "dram__bytes_read+write of both kernels per launch (8 x chunk calls), from profiles/r1_hough_accum_traffic.json",
+                         "algorithmic_bytes_per_launch": 10.0 * size * size * 8 * min(chunk, per_gpu),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
-                         "algorithmic_bytes_per_call": 10 * size * size, "ms_per_step": acc_ms},
+                         "algorithmic_bytes_per_call": 10 * size * size, "ms_per_step": acc_ms,
+                         "share_of_step": acc_ms / prof_ms_per_step},
             "cpu_baseline": cpu,
             "sections": sections,
+            "sections_pass": {"streams": 1, "ms_per_step": prof_ms_per_step,
+                              "note": "section timers and roofline come from a second pass of the same steps on one stream"},
             "check": {"bad_status": bad_status, "boards_not_equal_truth": wrong, "images_checked": per_gpu},
         }
         print(json.dumps(line), flush=True)
@@ -360,7 +387,7 @@ def main():
     ap.add_argument("--workload", default="synth1024", choices=sorted(WORKLOADS))
     ap.add_argument("--per-gpu", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
-    ap.add_argument("--streams", type=int, default=1)
+    ap.add_argument("--streams", type=int, default=2)
     ap.add_argument("--cpu-images", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

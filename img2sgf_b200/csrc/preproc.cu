@@ -258,28 +258,32 @@ template <int B> __global__ void __launch_bounds__(256) k_median(const uint8_t *
     constexpr int F = B + 3;                         // window columns of 4 adjacent pixels
     constexpr int RPW = 32 / F;                      // window rows packed per 32-bit word
     constexpr int NW = (B + RPW - 1) / RPW;          // words per window
+    constexpr int KM = (B * B) / 2 + 1;              // a value held by KM window pixels is the median
     __shared__ __align__(128) uint8_t s_in[SH * SW];
-    __shared__ uint32_t s_bits[8][SH][GW + 1];
+    __shared__ uint32_t s_bits[10][SH][GW + 1];      // planes 0..7: bits of the pixel; 8: pixel == 255; 9: pixel == 0
     __shared__ uint64_t s_bar;
     const size_t plane = (size_t)h * w;
     const uint8_t *img = src + blockIdx.z * plane;
     uint8_t *out = dst + blockIdx.z * plane;
     const int x0 = blockIdx.x * MT_W, y0 = blockIdx.y * MT_H;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     stage_tile_bulk(s_in, img, h, w, x0 - HX, y0 - R, SW, SH, BORDER_REPLICATE, bulk, al, &s_bar);
     {   // bit planes: s_bits[b][row][g] bit i = bit b of tile pixel (row, 32 g + i)
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         for (int u = warp; u < SH * GW; u += 8) {
             int row = u / GW, g = u - row * GW;
             int col = g * 32 + lane;
-            uint32_t px = col < SW ? s_in[row * SW + col] : 0u, mine = 0;
+            uint32_t px = col < SW ? s_in[row * SW + col] : 0x100u, mine = 0;
 #pragma unroll
             for (int bit = 0; bit < 8; bit++) {
                 uint32_t m = __ballot_sync(0xffffffffu, (px >> bit) & 1u);
                 if (lane == bit) mine = m;
             }
-            if (lane < 8) s_bits[lane][row][g] = mine;
+            const uint32_t m255 = __ballot_sync(0xffffffffu, px == 255u), m0 = __ballot_sync(0xffffffffu, px == 0u);
+            if (lane == 8) mine = m255;
+            if (lane == 9) mine = m0;
+            if (lane < 10) s_bits[lane][row][g] = mine;
         }
-        for (int i = threadIdx.x; i < 8 * SH; i += blockDim.x) s_bits[i / SH][i % SH][GW] = 0;   // pad word
+        for (int i = threadIdx.x; i < 10 * SH; i += blockDim.x) s_bits[i / SH][i % SH][GW] = 0;   // pad word
     }
     __syncthreads();
     // per-word masks of the B low bits of every packed row field
@@ -290,53 +294,81 @@ template <int B> __global__ void __launch_bounds__(256) k_median(const uint8_t *
 #pragma unroll
         for (int r = wd * RPW; r < B && r < (wd + 1) * RPW; r++) fm[wd] |= ((1u << B) - 1u) << ((r - wd * RPW) * F);
     }
-    for (int idx = threadIdx.x; idx < MT_H * (MT_W / 4); idx += blockDim.x) {
-        int ty = idx / (MT_W / 4), gx = (idx - ty * (MT_W / 4)) * 4;
-        int y = y0 + ty, x = x0 + gx;
-        if (y >= h || x >= w) continue;
+    // A warp covers a compact 16 x 8 pixel patch (lane = 4-pixel group lane%4 of row lane/4), so that
+    // the saturated-window shortcut below applies to whole warps as often as possible.
+    for (int q = warp; q < (MT_W / 16) * (MT_H / 8); q += 8) {
+        const int ty = (q / (MT_W / 16)) * 8 + (lane >> 2), gx = ((q % (MT_W / 16)) * 4 + (lane & 3)) * 4;
+        const int y = y0 + ty, x = x0 + gx;
+        const bool live = y < h && x < w;
         const int start = gx + HX - R, wi = start >> 5, sh = start & 31;
-        uint32_t P[8][NW];
+        // window bits of one plane for the 4 adjacent pixels: rows packed at a stride of F bits
+        auto gather = [&](int pl, uint32_t (&P)[NW]) {
 #pragma unroll
-        for (int bit = 0; bit < 8; bit++) {
-#pragma unroll
-            for (int wd = 0; wd < NW; wd++) P[bit][wd] = 0;
+            for (int wd = 0; wd < NW; wd++) P[wd] = 0;
 #pragma unroll
             for (int r = 0; r < B; r++) {
-                const uint32_t *rw = &s_bits[bit][ty + r][wi];
+                const uint32_t *rw = &s_bits[pl][ty + r][wi];
                 uint32_t bits = __funnelshift_r(rw[0], rw[1], sh) & ((1u << F) - 1u);
-                P[bit][r / RPW] |= bits << ((r % RPW) * F);
+                P[r / RPW] |= bits << ((r % RPW) * F);
             }
-        }
+        };
+        // Shortcut (exact): if at least KM of the B*B window pixels equal 255 the median is 255, likewise
+        // for 0.  Printed diagrams are mostly saturated paper and ink, so most warps finish here.
         uint32_t packed = 0;
+        bool open = false;                           // some pixel of this thread still needs the selection
+        {
+            uint32_t P255[NW], P0[NW];
+            gather(8, P255);
+            gather(9, P0);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            uint32_t C[NW];
-#pragma unroll
-            for (int wd = 0; wd < NW; wd++) C[wd] = fm[wd];
-            int k = (B * B) / 2;
-            uint32_t val = 0;
-#pragma unroll
-            for (int bit = 7; bit >= 0; bit--) {
-                uint32_t Z[NW], O[NW];
-                int nz = 0;
+            for (int j = 0; j < 4; j++) {
+                int c255 = 0, c0 = 0;
 #pragma unroll
                 for (int wd = 0; wd < NW; wd++) {
-                    uint32_t pj = P[bit][wd] >> j;
-                    Z[wd] = C[wd] & ~pj;
-                    O[wd] = C[wd] & pj;
-                    nz += __popc(Z[wd]);
+                    c255 += __popc((P255[wd] >> j) & fm[wd]);
+                    c0 += __popc((P0[wd] >> j) & fm[wd]);
                 }
-                const bool zero = k < nz;              // the median has a 0 in this bit
-#pragma unroll
-                for (int wd = 0; wd < NW; wd++) C[wd] = zero ? Z[wd] : O[wd];
-                if (!zero) { k -= nz; val |= 1u << bit; }
+                if (c255 >= KM) packed |= 0xffu << (8 * j);
+                else if (c0 < KM) open = true;
             }
-            packed |= val << (8 * j);
         }
-        size_t o = (size_t)y * w + x;
-        if (al && x + 3 < w) *reinterpret_cast<uint32_t *>(out + o) = packed;
-        else
-            for (int k2 = 0; k2 < 4 && x + k2 < w; k2++) out[o + k2] = (uint8_t)(packed >> (8 * k2));
+        if (__any_sync(0xffffffffu, open && live)) {
+            uint32_t P[8][NW];
+#pragma unroll
+            for (int bit = 0; bit < 8; bit++) gather(bit, P[bit]);
+            packed = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t C[NW];
+#pragma unroll
+                for (int wd = 0; wd < NW; wd++) C[wd] = fm[wd];
+                int k = (B * B) / 2;
+                uint32_t val = 0;
+#pragma unroll
+                for (int bit = 7; bit >= 0; bit--) {
+                    uint32_t Z[NW], O[NW];
+                    int nz = 0;
+#pragma unroll
+                    for (int wd = 0; wd < NW; wd++) {
+                        uint32_t pj = P[bit][wd] >> j;
+                        Z[wd] = C[wd] & ~pj;
+                        O[wd] = C[wd] & pj;
+                        nz += __popc(Z[wd]);
+                    }
+                    const bool zero = k < nz;              // the median has a 0 in this bit
+#pragma unroll
+                    for (int wd = 0; wd < NW; wd++) C[wd] = zero ? Z[wd] : O[wd];
+                    if (!zero) { k -= nz; val |= 1u << bit; }
+                }
+                packed |= val << (8 * j);
+            }
+        }
+        if (live) {
+            size_t o = (size_t)y * w + x;
+            if (al && x + 3 < w) *reinterpret_cast<uint32_t *>(out + o) = packed;
+            else
+                for (int k2 = 0; k2 < 4 && x + k2 < w; k2++) out[o + k2] = (uint8_t)(packed >> (8 * k2));
+        }
     }
 }
 
@@ -524,7 +556,8 @@ extern "C" int i2s_median(const uint8_t *src, uint8_t *dst, int n, int h, int w,
     } else if (b == 3) {
         k_median_net<3><<<grid, 256, 0, st>>>(src, dst, h, w, al, bulk);
     } else if (b == 5) {
-        k_median_net<5><<<grid, 256, 0, st>>>(src, dst, h, w, al, bulk);
+        if (legacy_enabled("med5bits")) k_median<5><<<grid, 256, 0, st>>>(src, dst, h, w, al, bulk);
+        else k_median_net<5><<<grid, 256, 0, st>>>(src, dst, h, w, al, bulk);
     } else {
         k_median<7><<<grid, 256, 0, st>>>(src, dst, h, w, al, bulk);
     }

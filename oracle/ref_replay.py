@@ -336,3 +336,39 @@ def load_enhanced(path: str) -> np.ndarray:
     """open_file (:651) + prologue (:142-150) at GUI defaults -> contrast-enhanced RGB array."""
     from PIL import Image
     return enhance(Image.open(path).convert('RGB'))
+
+
+# --------------------------------------------------------------------------- output stage
+# Replay of align_board (img2sgf.py:484-494) and to_SGF (:781-810) with the globals / Tk variable
+# turned into arguments; loops kept element by element like the reference (checker for
+# img2sgf_b200/sgf.py).
+ALIGN_TOP, ALIGN_BOTTOM, ALIGN_LEFT, ALIGN_RIGHT = range(4)
+
+
+def align_board(b, hsize, vsize, a=(ALIGN_LEFT, ALIGN_TOP)):
+    board = np.zeros((BOARD_SIZE, BOARD_SIZE))
+    xoffset = BOARD_SIZE - hsize if a[0] == ALIGN_RIGHT else 0
+    yoffset = BOARD_SIZE - vsize if a[1] == ALIGN_BOTTOM else 0
+    for i in range(hsize):
+        for j in range(vsize):
+            board[i + xoffset, j + yoffset] = b[i, j]
+    return board
+
+
+def to_SGF(board, side_to_move):
+    import string
+    letters = string.ascii_lowercase
+    lines = ["(;GM[1]FF[4]SZ[" + str(BOARD_SIZE) + "]", "PL[B]" if side_to_move == 1 else "PL[W]"]
+    moves = {}
+    for colour, tag in ((1, "AB"), (2, "AW")):
+        text = ""
+        if colour in board:
+            text = tag
+            for i in range(BOARD_SIZE):
+                for j in range(BOARD_SIZE):
+                    if board[i, j] == colour:
+                        text += "[" + letters[i] + letters[j] + "]"
+        moves[colour] = text
+    order = (1, 2) if side_to_move == 1 else (2, 1)
+    lines += [moves[order[0]], moves[order[1]], ")"]
+    return "\n".join(lines) + "\n"

@@ -71,6 +71,26 @@ def test_primitives_odd_shapes(api, oracle, shape):
         assert_same(api.median_blur(g, b), oracle.median(g, b), f"median{b}")
 
 
+@pytest.mark.parametrize("size,noise", [(400, 0.0), (333, 0.0), (512, 3.0)])
+def test_primitives_saturated_diagrams(api, oracle, size, noise):
+    """Diagram-like content (saturated paper / ink, anti-aliased rims): exercises the saturated-window
+    shortcut of the 7x7 median on whole warps, partially resolved warps, and noisy content where it
+    never applies; plus both Cannys and the Gaussians on the same arrays."""
+    from img2sgf_b200 import synth
+    g, _ = synth.diagram(size, 20, 9, seed=size, noise=noise)
+    g = np.ascontiguousarray(g)
+    inv = np.ascontiguousarray(255 - g)                       # ink-dominated windows (pixel == 0 branch)
+    half = g.copy(); half[:, size // 2:] = 0                  # a long straight 255 | 0 boundary
+    for name, img in (("diagram", g), ("inverted", inv), ("half", half)):
+        for b in (3, 5, 7):
+            assert_same(api.median_blur(img, b), oracle.median(img, b), f"{name} median{b}")
+        for b, got in zip((3, 5, 7), api.gaussian_blurs(img)):
+            assert_same(got, oracle.gauss(img, b), f"{name} gauss{b}")
+        assert_same(api.canny_grey(img), oracle.canny_grey(img), f"{name} canny_grey")
+    rgb = synth.to_rgb(g)
+    assert_same(api.edge_map(rgb), oracle.canny_rgb(rgb), "canny_rgb")
+
+
 def test_canny_long_chain_needs_many_passes(api, oracle):
     """A weak spiral seeded by one strong pixel crosses many 128-px tiles: exercises the
     cross-tile hysteresis passes and the status/retry path."""
