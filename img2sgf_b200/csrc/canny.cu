@@ -227,9 +227,9 @@ __global__ void __launch_bounds__(CR_WARPS * 32, MINB) k_canny_roll(const MapSet
                     canny_load<CH>(img + (size_t)min(max(py + 1, 0), h - 1) * w * CH, x, w, al, nxt);
 #pragma unroll
                     for (int c = 0; c < CH; c++) {
-                        const uint32_t xl = __shfl_up_sync(0xffffffffu, ch[c], 1) >> 24;
-                        const uint32_t xr = __shfl_down_sync(0xffffffffu, ch[c], 1);
-                        R[u % 3][c] = roll::sobel_row(ch[c], xl, xr);
+                        const uint32_t lw = __shfl_up_sync(0xffffffffu, ch[c], 1);
+                        const uint32_t rw = __shfl_down_sync(0xffffffffu, ch[c], 1);
+                        R[u % 3][c] = roll::sobel_row(ch[c], lw, rw);
                     }
                 }
                 if (it >= 2) {                                 // gradient + magnitude of row gy = py - 1

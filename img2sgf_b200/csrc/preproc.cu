@@ -268,22 +268,29 @@ template <int B> __global__ void __launch_bounds__(256) k_median(const uint8_t *
     const int x0 = blockIdx.x * MT_W, y0 = blockIdx.y * MT_H;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     stage_tile_bulk(s_in, img, h, w, x0 - HX, y0 - R, SW, SH, BORDER_REPLICATE, bulk, al, &s_bar);
-    {   // bit planes: s_bits[b][row][g] bit i = bit b of tile pixel (row, 32 g + i)
-        for (int u = warp; u < SH * GW; u += 8) {
-            int row = u / GW, g = u - row * GW;
-            int col = g * 32 + lane;
-            uint32_t px = col < SW ? s_in[row * SW + col] : 0x100u, mine = 0;
+    {   // bit planes: s_bits[b][row][g] bit i = bit b of tile pixel (row, 32 g + i).  A thread turns
+        // 8 adjacent pixels into one byte of every plane: bit b of the 4 bytes of a word is gathered
+        // into a nibble by one multiply ((x & 0x01010101) * 0x01020408 puts byte j's bit at 24 + j).
+        static_assert(SW % 8 == 0, "whole bytes of a plane row");
+        uint8_t *planes = reinterpret_cast<uint8_t *>(&s_bits[0][0][0]);
+        constexpr int ROWB = (GW + 1) * 4, PLB = SH * ROWB;           // bytes per plane row / per plane
+        auto nib = [](uint32_t v) { return ((v & 0x01010101u) * 0x01020408u) >> 24; };
+        auto all8 = [](uint32_t v) { v &= v >> 1; v &= v >> 2; v &= v >> 4; return v; };   // bit 0 of each byte: byte == 0xff
+        for (int i = threadIdx.x; i < SH * (SW / 8); i += blockDim.x) {
+            const int row = i / (SW / 8), k = i - row * (SW / 8);
+            const uint2 v = *reinterpret_cast<const uint2 *>(s_in + row * SW + 8 * k);
+            uint8_t *dstb = planes + row * ROWB + k;
 #pragma unroll
-            for (int bit = 0; bit < 8; bit++) {
-                uint32_t m = __ballot_sync(0xffffffffu, (px >> bit) & 1u);
-                if (lane == bit) mine = m;
-            }
-            const uint32_t m255 = __ballot_sync(0xffffffffu, px == 255u), m0 = __ballot_sync(0xffffffffu, px == 0u);
-            if (lane == 8) mine = m255;
-            if (lane == 9) mine = m0;
-            if (lane < 10) s_bits[lane][row][g] = mine;
+            for (int bit = 0; bit < 8; bit++) dstb[bit * PLB] = (uint8_t)(nib(v.x >> bit) | (nib(v.y >> bit) << 4));
+            dstb[8 * PLB] = (uint8_t)(nib(all8(v.x)) | (nib(all8(v.y)) << 4));
+            dstb[9 * PLB] = (uint8_t)(nib(all8(~v.x)) | (nib(all8(~v.y)) << 4));
         }
         for (int i = threadIdx.x; i < 10 * SH; i += blockDim.x) s_bits[i / SH][i % SH][GW] = 0;   // pad word
+        if (SW % 32 != 0)                                             // bytes of the last word beyond the tile
+            for (int i = threadIdx.x; i < 10 * SH * (4 - (SW / 8) % 4); i += blockDim.x) {
+                const int pr = i / (4 - (SW / 8) % 4), kk = SW / 8 + i % (4 - (SW / 8) % 4);
+                planes[pr * ROWB + kk] = 0;
+            }
     }
     __syncthreads();
     // per-word masks of the B low bits of every packed row field

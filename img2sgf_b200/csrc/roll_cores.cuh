@@ -123,19 +123,19 @@ I2S_HD uint32_t gauss_h7(uint32_t Em2, uint32_t Em1, uint32_t E0, uint32_t E1, u
 }
 
 // ------------------------------------------------------------------ Sobel + L1 magnitude (A.4)
-// One pixel row of one channel, seen by a lane: its own word plus the pixel left of it (xl) and
-// right of it (xr).  Kept per row: the three shifted pairs Nm = (p-1,p0), No = (p1,p2),
+// One pixel row of one channel, seen by a lane: its own word plus the words of the two neighbour lanes.  Kept per row: the three shifted pairs Nm = (p-1,p0), No = (p1,p2),
 // Np = (p3,p4) and the horizontal smoothing sA = (s0,s1), sB = (s2,s3), s_j = p[j-1]+2p[j]+p[j+1].
 struct SobelRow { uint32_t Nm, No, Np, sA, sB; };
 
-I2S_HD SobelRow sobel_row(uint32_t word, uint32_t xl, uint32_t xr)
+I2S_HD SobelRow sobel_row(uint32_t word, uint32_t left_word, uint32_t right_word)
 {
+    // left_word / right_word: the neighbour lanes' words of the same row (p-1 = byte 3 of the left
+    // one, p4 = byte 0 of the right one); the zero bytes of the unpacked pairs serve as zero source
     const uint32_t lo = pair_lo(word), hi = pair_hi(word);
-    const uint32_t x = (xl & 0xffu) | ((xr & 0xffu) << 16);          // (p-1, p4)
     SobelRow r;
-    r.Nm = prmt(x, lo, 0x5410);
-    r.No = pair_mid(lo, hi);
-    r.Np = prmt(hi, x, 0x7632);
+    r.Nm = prmt(left_word, lo, 0x5453);        // (p-1, p0)
+    r.No = pair_mid(lo, hi);                   // (p1, p2)
+    r.Np = prmt(hi, right_word, 0x1412);       // (p3, p4)
     r.sA = r.Nm + r.No + lo + lo;
     r.sB = r.No + r.Np + hi + hi;
     return r;
@@ -186,10 +186,9 @@ I2S_HD MagRow mag_row(uint32_t A, uint32_t B, uint32_t leftB, uint32_t rightA)
 {
     MagRow r;
     r.A = A; r.B = B;
-    const uint32_t x = prmt(leftB, rightA, 0x5432);            // (m-1, m4)
-    r.Cm = prmt(x, A, 0x5410);
+    r.Cm = pair_mid(leftB, A);                 // (left lane's m3, m0)
     r.Co = pair_mid(A, B);
-    r.Cp = prmt(B, x, 0x7632);
+    r.Cp = pair_mid(B, rightA);                // (m3, right lane's m0)
     return r;
 }
 

@@ -102,9 +102,9 @@ extern "C" void rh_sobel_nms(const uint8_t *src, int ch, int h, int w, int low, 
                     }
                     for (int lane = 0; lane < 32; lane++)
                         for (int c = 0; c < ch; c++) {
-                            uint32_t xl = (lane > 0 ? word[lane - 1][c] : word[lane][c]) >> 24;      // shfl_up keeps own value at lane 0
-                            uint32_t xr = lane < 31 ? word[lane + 1][c] : word[lane][c];
-                            R[lane][u % 3][c] = sobel_row(word[lane][c], xl, xr);
+                            uint32_t lw = lane > 0 ? word[lane - 1][c] : word[lane][c];      // shfl_up keeps own value at lane 0
+                            uint32_t rw = lane < 31 ? word[lane + 1][c] : word[lane][c];
+                            R[lane][u % 3][c] = sobel_row(word[lane][c], lw, rw);
                         }
                     uint32_t mA[32], mB[32];
                     if (it >= 2) {

@@ -77,7 +77,7 @@ def test_primitives_saturated_diagrams(api, oracle, size, noise):
     shortcut of the 7x7 median on whole warps, partially resolved warps, and noisy content where it
     never applies; plus both Cannys and the Gaussians on the same arrays."""
     from img2sgf_b200 import synth
-    g, _ = synth.diagram(size, 20, 9, seed=size, noise=noise)
+    g, _ = synth.diagram(size, 16, 7, seed=size, noise=noise)
     g = np.ascontiguousarray(g)
     inv = np.ascontiguousarray(255 - g)                       # ink-dominated windows (pixel == 0 branch)
     half = g.copy(); half[:, size // 2:] = 0                  # a long straight 255 | 0 boundary
