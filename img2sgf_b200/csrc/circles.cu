@@ -619,7 +619,8 @@ __global__ void __launch_bounds__(256) k_circles_finish(const unsigned long long
 __constant__ int c_call_map[I2S_N_CALLS] = {0, 1, 0, 0, 2, 3, 4, 5, 6, 7};
 
 __global__ void __launch_bounds__(256) k_stack(const float *__restrict__ mcirc, const int32_t *__restrict__ mcount,
-                                               int n, int circle_cap, float *out, int32_t *counts, int32_t *status)
+                                               int n, int circle_cap, float *out, int32_t *counts, int32_t *status,
+                                               int2 *dup)
 {
     const int img = blockIdx.x;
     int off = 0;
@@ -635,6 +636,10 @@ __global__ void __launch_bounds__(256) k_stack(const float *__restrict__ mcirc, 
     if (threadIdx.x == 0) {
         counts[img] = off;
         if (off > circle_cap) atomicOr(status + img, I2S_ST_CIRCLE_OVERFLOW);
+        // calls 0, 2 and 3 are the same list (grey, median 1, Gaussian 1): k_mask may ignore the first
+        // two copies, the third one covers the same pixels later in the sequence
+        const int n0 = min(mcount[img], circle_cap), n1 = min(mcount[n + img], circle_cap);
+        dup[img] = (off <= circle_cap) ? make_int2(n0, n1) : make_int2(0, 0);
     }
 }
 
@@ -653,7 +658,8 @@ __device__ __forceinline__ void circle_rect(const float *c, int &x0, int &y0, in
 
 __global__ void __launch_bounds__(256) k_mask(const uint8_t *__restrict__ edges, uint8_t *__restrict__ masked, int h,
                                               int w, const float *__restrict__ circles,
-                                              const int32_t *__restrict__ counts, int circle_cap)
+                                              const int32_t *__restrict__ counts, int circle_cap,
+                                              const int2 *__restrict__ dup)
 {
     __shared__ short4 s_rect[KCHUNK];
     __shared__ int s_idx[KCHUNK];
@@ -662,6 +668,9 @@ __global__ void __launch_bounds__(256) k_mask(const uint8_t *__restrict__ edges,
     const size_t plane = (size_t)h * w;
     const float *circ = circles + (size_t)img * circle_cap * 3;
     const int n = min(counts[img], circle_cap);
+    // circles [0, n0) and [n0 + n1, 2 n0 + n1) are repeated verbatim at [2 n0 + n1, 3 n0 + n1) (see k_stack)
+    const int2 dd = dup ? dup[img] : make_int2(0, 0);
+    const int skip_a = dd.x, skip_b0 = dd.x + dd.y, skip_b1 = 2 * dd.x + dd.y;
     const int tx0 = blockIdx.x * KT, ty0 = blockIdx.y * KT;
     const int tx1 = min(tx0 + KT, w) - 1, ty1 = min(ty0 + KT, h) - 1;
     int last[16];
@@ -674,6 +683,7 @@ __global__ void __launch_bounds__(256) k_mask(const uint8_t *__restrict__ edges,
         if (threadIdx.x == 0) s_n = 0;
         __syncthreads();
         for (int i = c0 + threadIdx.x; i < min(n, c0 + KCHUNK); i += blockDim.x) {
+            if (i < skip_a || (i >= skip_b0 && i < skip_b1)) continue;
             int x0, y0, x1, y1;
             circle_rect(circ + 3 * i, x0, y0, x1, y1);
             if (x1 >= tx0 && x0 <= tx1 && y1 >= ty0 && y0 <= ty1) {
@@ -795,10 +805,10 @@ int hough_circles_maps(const MapSet &ms, int h, int w, float *mcirc, int32_t *mc
 }
 
 int mask_circles(const uint8_t *edges, uint8_t *masked, int n, int h, int w, const float *circles,
-                 const int32_t *counts, int circle_cap, cudaStream_t st)
+                 const int32_t *counts, int circle_cap, cudaStream_t st, const int2 *dup)
 {
     ScopedSection sec(SEC_MASK, st);
-    k_mask<<<dim3(cdiv(w, KT), cdiv(h, KT), n), 256, 0, st>>>(edges, masked, h, w, circles, counts, circle_cap);
+    k_mask<<<dim3(cdiv(w, KT), cdiv(h, KT), n), 256, 0, st>>>(edges, masked, h, w, circles, counts, circle_cap, dup);
     I2S_CHECK_LAUNCH("k_mask");
     return I2S_OK;
 }
@@ -809,6 +819,7 @@ size_t find_circles_scratch_bytes(int n, int h, int w, const i2s_limits_t &lim)
     size_t b = 6 * align_up((size_t)n * plane, 256);                       // the six blurred copies
     b += align_up((size_t)n * I2S_N_UNIQUE * lim.circle_cap * 12, 256);    // per-map circles
     b += align_up((size_t)n * I2S_N_UNIQUE * 4, 256);
+    b += align_up((size_t)n * sizeof(int2), 256);
     return b + circles_scratch_bytes(n * I2S_N_UNIQUE, h, w, lim) + 4096;
 }
 
@@ -821,6 +832,7 @@ int find_circles(const uint8_t *grey, const uint8_t *edges, int n, int h, int w,
     const int maps = n * I2S_N_UNIQUE;
     float *mcirc = ar.take<float>((size_t)maps * lim.circle_cap * 3);
     int32_t *mcount = ar.take<int32_t>(maps);
+    int2 *dup = ar.take<int2>(n);
     if (!ar.ok()) { set_error("find_circles: workspace too small"); return I2S_E_WORKSPACE; }
     // internal order: grey, edges, med3, gau3, med5, gau5, med7, gau7
     int rc;
@@ -835,10 +847,10 @@ int find_circles(const uint8_t *grey, const uint8_t *edges, int n, int h, int w,
     if ((rc = hough_circles_maps(ms, h, w, mcirc, mcount, status, lim, ar, st))) return rc;
     {
         ScopedSection sec(SEC_STACK, st);
-        k_stack<<<n, 256, 0, st>>>(mcirc, mcount, n, lim.circle_cap, circles, counts, status);
+        k_stack<<<n, 256, 0, st>>>(mcirc, mcount, n, lim.circle_cap, circles, counts, status, dup);
         I2S_CHECK_LAUNCH("k_stack");
     }
-    return mask_circles(edges, masked, n, h, w, circles, counts, lim.circle_cap, st);
+    return mask_circles(edges, masked, n, h, w, circles, counts, lim.circle_cap, st, legacy_enabled("mask") ? nullptr : dup);
 }
 
 }  // namespace i2s
@@ -875,7 +887,7 @@ extern "C" int i2s_mask_circles(const uint8_t *edges, uint8_t *masked, int n, in
 {
     I2S_ARG(edges && masked && circles && counts && n >= 0 && h > 0 && w > 0 && circle_cap > 0);
     if (n == 0) return I2S_OK;
-    return mask_circles(edges, masked, n, h, w, circles, counts, circle_cap, (cudaStream_t)stream);
+    return mask_circles(edges, masked, n, h, w, circles, counts, circle_cap, (cudaStream_t)stream, nullptr);
 }
 
 extern "C" size_t i2s_find_circles_workspace_bytes(int n, int h, int w, const i2s_limits_t *lim)

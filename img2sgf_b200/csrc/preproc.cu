@@ -563,8 +563,9 @@ extern "C" int i2s_median(const uint8_t *src, uint8_t *dst, int n, int h, int w,
     } else if (b == 3) {
         k_median_net<3><<<grid, 256, 0, st>>>(src, dst, h, w, al, bulk);
     } else if (b == 5) {
-        if (legacy_enabled("med5bits")) k_median<5><<<grid, 256, 0, st>>>(src, dst, h, w, al, bulk);
-        else k_median_net<5><<<grid, 256, 0, st>>>(src, dst, h, w, al, bulk);
+        // bit planes + saturated-window shortcut beat the 99-exchange network on diagram content
+        if (legacy_enabled("med5net")) k_median_net<5><<<grid, 256, 0, st>>>(src, dst, h, w, al, bulk);
+        else k_median<5><<<grid, 256, 0, st>>>(src, dst, h, w, al, bulk);
     } else {
         k_median<7><<<grid, 256, 0, st>>>(src, dst, h, w, al, bulk);
     }
