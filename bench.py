@@ -292,23 +292,36 @@ def run_ours(args, rank, world, local_rank):
     e2e = None
     if not args.no_e2e:
         copy_stream = torch.cuda.Stream()
-        bufs = [torch.empty((chunk, size, size, 3), dtype=torch.uint8, device="cuda") for _ in range(2)]
-        done = [torch.cuda.Event(), torch.cuda.Event()]
+        engines = runner.engines
+        comp = runner.streams                       # None: everything on the current stream
+        S = len(engines)
+        nbuf = 2 * S                                # two staging buffers per compute stream
+        bufs = [torch.empty((chunk, size, size, 3), dtype=torch.uint8, device="cuda") for _ in range(nbuf)]
+        ready = [torch.cuda.Event() for _ in range(nbuf)]
+        done = [torch.cuda.Event() for _ in range(nbuf)]
         host_rec = torch.empty((total, B.RECORD_BYTES), dtype=torch.uint8).pin_memory()
 
         def step_e2e():
             main = torch.cuda.current_stream()
+            if comp:
+                for st in comp:
+                    st.wait_stream(main)
             for k, s in enumerate(range(0, per_gpu, chunk)):
                 e = min(per_gpu, s + chunk)
-                b = k & 1
+                b = k % nbuf
                 with torch.cuda.stream(copy_stream):
-                    if k >= 2:
-                        copy_stream.wait_event(done[b])
+                    if k >= nbuf:
+                        copy_stream.wait_event(done[b])        # the kernels that read this buffer have finished
                     bufs[b][:e - s].copy_(host[s:e], non_blocking=True)
-                    ready = torch.cuda.Event(); ready.record(copy_stream)
-                main.wait_event(ready)
-                runner.engine.run(bufs[b][:e - s], thr, 128, n=e - s, records_out=records[s:e])
-                done[b].record(main)
+                    ready[b].record(copy_stream)
+                cs = comp[k % S] if comp else main
+                cs.wait_event(ready[b])
+                with torch.cuda.stream(cs):
+                    engines[k % S].run(bufs[b][:e - s], thr, 128, n=e - s, records_out=records[s:e])
+                    done[b].record(cs)
+            if comp:
+                for st in comp:
+                    main.wait_stream(st)
             full = B.gather_records(records, total)
             host_rec.copy_(full, non_blocking=True)
             torch.cuda.synchronize()

@@ -279,16 +279,14 @@ constexpr int HX = 16;                            // staged x halo: rows are 16-
 constexpr int HS_W = HT + 2 * HX, HS_H = HT + 2;  // y halo 1
 constexpr int HQ = (HT + 2) * (HT + 2);
 
-__global__ void __launch_bounds__(256) k_hysteresis(uint8_t *__restrict__ state, int h, int w, int tiles_x,
-                                                    int tiles_y, uint8_t *dirty_in, uint8_t *dirty_out,
-                                                    int pass, bool al, bool bulk)
+// One tile.  `tile` = (map * tiles_y + ty) * tiles_x + tx.  `phase` counts the uses of the block's
+// mbarrier (its parity is what a waiter passes).  Returns with all threads (uniform control flow).
+__device__ __forceinline__ void hyst_tile(uint8_t *__restrict__ state, int h, int w, int tiles_x, int tiles_y,
+                                          uint8_t *dirty_in, uint8_t *dirty_out, int pass, bool al, bool bulk,
+                                          int tile, uint8_t *s_map, uint16_t *s_q, int &s_qn, int &s_changed,
+                                          int &s_ring, uint64_t &s_bar, uint32_t &phase)
 {
-    extern __shared__ __align__(16) uint8_t s_dyn[];
-    uint8_t *s_map = s_dyn;                                              // HS_H * HS_W bytes
-    uint16_t *s_q = reinterpret_cast<uint16_t *>(s_dyn + HS_H * HS_W);   // HQ entries
-    __shared__ int s_qn, s_changed, s_ring;
-    __shared__ uint64_t s_bar;
-    const int tile = (blockIdx.z * tiles_y + blockIdx.y) * tiles_x + blockIdx.x;
+    const int bx = tile % tiles_x, by = (tile / tiles_x) % tiles_y, bz = tile / (tiles_x * tiles_y);
     if (pass > 0) {
         const int d = dirty_in[tile];
         __syncthreads();                               // everyone has read the flag before it is cleared
@@ -296,8 +294,8 @@ __global__ void __launch_bounds__(256) k_hysteresis(uint8_t *__restrict__ state,
         if (threadIdx.x == 0) dirty_in[tile] = 0;      // leave the buffer clean for pass+1's writers
     }
     const size_t plane = (size_t)h * w;
-    uint8_t *img = state + blockIdx.z * plane;
-    const int x0 = blockIdx.x * HT, y0 = blockIdx.y * HT;
+    uint8_t *img = state + bz * plane;
+    const int x0 = bx * HT, y0 = by * HT;
     if (threadIdx.x == 0) { s_qn = 0; s_changed = 0; s_ring = 0; }
     if (bulk) {
         // in-image part of every staged row with one bulk copy per row; the rest (tiles on the image
@@ -305,8 +303,6 @@ __global__ void __launch_bounds__(256) k_hysteresis(uint8_t *__restrict__ state,
         const int cxa = max(x0 - HX, 0), cxb = min(x0 + HT + HX, w);
         const int ra = max(0, 1 - y0), rb = min(HS_H, h - y0 + 1);          // staged rows [ra, rb) lie in the image
         const int off = cxa - (x0 - HX);
-        if (threadIdx.x == 0) mbar_init(&s_bar, 1);
-        __syncthreads();
         if (threadIdx.x < 32) {
             if (threadIdx.x == 0) mbar_arrive_expect_tx(&s_bar, (uint32_t)((rb - ra) * (cxb - cxa)));
             for (int r = ra + threadIdx.x; r < rb; r += 32)
@@ -319,7 +315,8 @@ __global__ void __launch_bounds__(256) k_hysteresis(uint8_t *__restrict__ state,
                 if (r < ra || r >= rb || c < wa || c >= wb) reinterpret_cast<uint32_t *>(s_map)[idx] = 0u;
             }
         }
-        mbar_wait(&s_bar, 0);
+        mbar_wait(&s_bar, phase & 1u);
+        phase++;
     } else {
         stage_tile_u8(s_map, HS_W, img, h, w, x0 - HX, y0 - 1, HS_W, HS_H, BORDER_ZERO, al);
     }
@@ -391,9 +388,33 @@ __global__ void __launch_bounds__(256) k_hysteresis(uint8_t *__restrict__ state,
     }
     if (s_ring && threadIdx.x < 9) {
         int dy = threadIdx.x / 3 - 1, dx = threadIdx.x % 3 - 1;
-        int ty = blockIdx.y + dy, tx = blockIdx.x + dx;
+        int ty = by + dy, tx = bx + dx;
         if ((dx || dy) && ty >= 0 && ty < tiles_y && tx >= 0 && tx < tiles_x)
-            dirty_out[(blockIdx.z * tiles_y + ty) * tiles_x + tx] = 1;
+            dirty_out[(bz * tiles_y + ty) * tiles_x + tx] = 1;
+    }
+}
+
+// Pass 0 visits every tile (one per block).  Later passes only continue tiles flagged dirty, which
+// are few: a block then looks after `tiles_per_block` consecutive tiles, so that a pass over a
+// mostly clean map costs an eighth of the block launches.
+__global__ void __launch_bounds__(256) k_hysteresis(uint8_t *__restrict__ state, int h, int w, int tiles_x,
+                                                    int tiles_y, int total_tiles, int tiles_per_block,
+                                                    uint8_t *dirty_in, uint8_t *dirty_out, int pass, bool al, bool bulk)
+{
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    uint8_t *s_map = s_dyn;                                              // HS_H * HS_W bytes
+    uint16_t *s_q = reinterpret_cast<uint16_t *>(s_dyn + HS_H * HS_W);   // HQ entries
+    __shared__ int s_qn, s_changed, s_ring;
+    __shared__ uint64_t s_bar;
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    uint32_t phase = 0;
+    for (int k = 0; k < tiles_per_block; k++) {
+        const int tile = blockIdx.x * tiles_per_block + k;
+        if (tile >= total_tiles) break;
+        hyst_tile(state, h, w, tiles_x, tiles_y, dirty_in, dirty_out, pass, al, bulk, tile, s_map, s_q, s_qn, s_changed,
+                  s_ring, s_bar, phase);
+        __syncthreads();                                                 // shared state is reused by the next tile
     }
 }
 
@@ -475,8 +496,8 @@ int hysteresis(uint8_t *state, int maps, int n_images, int h, int w, int passes,
     size_t tiles = (size_t)maps * tx * ty;
     uint8_t *d0 = (uint8_t *)scratch, *d1 = d0 + align_up(tiles, 256);
     I2S_CUDA(cudaMemsetAsync(d0, 0, align_up(tiles, 256) * 2, st));
-    dim3 g(tx, ty, maps);
     if (passes < 1) passes = 1;
+    I2S_ARG(tiles < (1ull << 31));
     constexpr int kSmem = HS_H * HS_W + HQ * 2;
     static bool attr_done = false;
     if (!attr_done) {
@@ -485,7 +506,9 @@ int hysteresis(uint8_t *state, int maps, int n_images, int h, int w, int passes,
     }
     for (int p = 0; p < passes; p++) {
         uint8_t *din = (p & 1) ? d1 : d0, *dout = (p & 1) ? d0 : d1;
-        k_hysteresis<<<g, 256, kSmem, st>>>(state, h, w, tx, ty, din, dout, p, al, bulk);
+        const int tpb = p == 0 ? 1 : 8;
+        k_hysteresis<<<(unsigned)((tiles + tpb - 1) / tpb), 256, kSmem, st>>>(state, h, w, tx, ty, (int)tiles, tpb, din, dout,
+                                                                             p, al, bulk);
         I2S_CHECK_LAUNCH("k_hysteresis");
     }
     uint8_t *last = (passes & 1) ? d1 : d0;   // buffer written by the final pass

@@ -329,19 +329,16 @@ __device__ __forceinline__ void vote_item(int *s_acc, uint2 e, int cx0, int cy0,
         lo = fmaxf(lo, fminf(ta, tb)); hi = fminf(hi, fmaxf(ta, tb));
     } else if (y < Y0 || y > Y1) return;
     const int t_lo = max(-MAX_R, (int)floorf(lo - 0.25f)), t_hi = min(MAX_R, (int)ceilf(hi + 0.25f));
+    if (t_lo > t_hi) return;
+    // Both rays are one arithmetic sequence in the signed radius t: cell(t) = floor((p*1024 + t*step) / 1024)
+    // for t > 0 (forward) and t < 0 (backward, r = -t).  One loop over t_lo..t_hi votes them all -- a warp
+    // then runs max(len) instead of max(forward) + max(backward) -- and the vote the loop casts at t = 0
+    // (the pixel's own cell, which the reference never votes) is taken back afterwards.
     const int xb = (x - cx0) * 1024, yb = (y - cy0) * 1024;
-    {
-        const int r0 = max(t_lo, MIN_R);
-        int x1 = xb + r0 * sx, y1 = yb + r0 * sy;
+    int x1 = xb + t_lo * sx, y1 = yb + t_lo * sy;
 #pragma unroll 4
-        for (int r = r0; r <= t_hi; r++, x1 += sx, y1 += sy) atomicAdd(s_acc + (y1 >> 10) * AP + (x1 >> 10), 1);
-    }
-    {
-        const int r0 = max(-t_hi, MIN_R), r1 = -t_lo;
-        int x1 = xb - r0 * sx, y1 = yb - r0 * sy;
-#pragma unroll 4
-        for (int r = r0; r <= r1; r++, x1 -= sx, y1 -= sy) atomicAdd(s_acc + (y1 >> 10) * AP + (x1 >> 10), 1);
-    }
+    for (int t = t_lo; t <= t_hi; t++, x1 += sx, y1 += sy) atomicAdd(s_acc + (y1 >> 10) * AP + (x1 >> 10), 1);
+    if (t_lo <= 0 && t_hi >= 0) atomicAdd(s_acc + (y - cy0) * AP + (x - cx0), -1);
 }
 
 __global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks2(const uint2 *__restrict__ edges,
