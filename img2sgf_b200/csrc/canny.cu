@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) k_sobel_nms(const MapSet ms, uint8_t *__r
 // instruction), two shuffles of the magnitudes and the branch-free packed NMS of the row two
 // above (roll_cores.cuh).  The diagonal-sector test runs only when some lane of the warp has a
 // diagonal candidate.  No shared memory, no barriers.
-constexpr int CR_TH = 64, CR_OW = 120, CR_WARPS = 4;
+constexpr int CR_TH = 128, CR_OW = 120, CR_WARPS = 4;   // 4 warm-up rows per 128-row strip
 
 template <int CH>
 __device__ __forceinline__ void canny_load(const uint8_t *__restrict__ row, int x, int w, bool al, uint32_t (&ch)[CH])
@@ -394,9 +394,8 @@ __device__ __forceinline__ void hyst_tile(uint8_t *__restrict__ state, int h, in
     }
 }
 
-// Pass 0 visits every tile (one per block).  Later passes only continue tiles flagged dirty, which
-// are few: a block then looks after `tiles_per_block` consecutive tiles, so that a pass over a
-// mostly clean map costs an eighth of the block launches.
+// A block looks after `tiles_per_block` consecutive tiles (1 in production: several per block on the
+// later, mostly clean passes saves block launches but serialises the dirty tiles -- measured slower).
 __global__ void __launch_bounds__(256) k_hysteresis(uint8_t *__restrict__ state, int h, int w, int tiles_x,
                                                     int tiles_y, int total_tiles, int tiles_per_block,
                                                     uint8_t *dirty_in, uint8_t *dirty_out, int pass, bool al, bool bulk)
@@ -478,7 +477,10 @@ int canny_states(const MapSet &ms, int channels, uint8_t *state, int h, int w, i
             else
                 k_canny_roll<1, 6><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total);
         } else {
-            k_canny_roll<3, 4><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total);
+            if (legacy_enabled("rgb5"))
+                k_canny_roll<3, 5><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total);
+            else
+                k_canny_roll<3, 4><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total);
         }
     }
     I2S_CHECK_LAUNCH("k_sobel_nms");
@@ -506,7 +508,7 @@ int hysteresis(uint8_t *state, int maps, int n_images, int h, int w, int passes,
     }
     for (int p = 0; p < passes; p++) {
         uint8_t *din = (p & 1) ? d1 : d0, *dout = (p & 1) ? d0 : d1;
-        const int tpb = p == 0 ? 1 : 8;
+        const int tpb = (p > 0 && legacy_enabled("hyst8")) ? 8 : 1;   // 8 tiles per block measured slower: dirty tiles then run one after another
         k_hysteresis<<<(unsigned)((tiles + tpb - 1) / tpb), 256, kSmem, st>>>(state, h, w, tx, ty, (int)tiles, tpb, din, dout,
                                                                              p, al, bulk);
         I2S_CHECK_LAUNCH("k_hysteresis");

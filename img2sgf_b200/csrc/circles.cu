@@ -361,7 +361,11 @@ __global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks2(const uint2 *__res
     const int ry0 = max(ty0 - 1 - MAX_R, 0), ry1 = min(ty0 + AT + MAX_R, h - 1);
     const int bx0 = rx0 / EB, bx1 = rx1 / EB, by0 = ry0 / EB, by1 = ry1 / EB;
     const int nbw = bx1 - bx0 + 1, nb = nbw * (by1 - by0 + 1);      // <= VB*VB
-    for (int i = threadIdx.x; i < AS * AP; i += blockDim.x) s_acc[i] = 0;
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(s_acc);                   // 16-byte stores; the tail word by word
+        for (int i = threadIdx.x; i < AS * AP / 4; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+        for (int i = (AS * AP / 4) * 4 + threadIdx.x; i < AS * AP; i += blockDim.x) s_acc[i] = 0;
+    }
     if (threadIdx.x < nb) {
         const int b = threadIdx.x;
         const int2 d = dir[((size_t)map * nby + by0 + b / nbw) * nbx + bx0 + b % nbw];
@@ -397,12 +401,14 @@ __global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks2(const uint2 *__res
         }
     }
     __syncthreads();
-    if (cx0 < 0 || cy0 < 0 || cx0 + AS > w || cy0 + AS > h) {
-        for (int i = threadIdx.x; i < AS * AS; i += blockDim.x) {
-            int ly = i / AS, lx = i - ly * AS;
-            int cx = cx0 + lx, cy = cy0 + ly;
-            if (cx < 0 || cy < 0 || cx >= w || cy >= h) s_acc[ly * AP + lx] = 0;
-        }
+    // Cells outside the image never receive votes in the reference.  The conservative extra step can
+    // leave a vote at most one cell outside the clip box; of those cells the peak test below only ever
+    // reads column w and row h (right / lower neighbours of the last column / row): clear them.
+    if (w - cx0 < AS || h - cy0 < AS) {
+        if (w - cx0 < AS)
+            for (int ly = threadIdx.x; ly < AS; ly += blockDim.x) s_acc[ly * AP + (w - cx0)] = 0;
+        if (h - cy0 < AS)
+            for (int lx = threadIdx.x; lx < AS; lx += blockDim.x) s_acc[(h - cy0) * AP + lx] = 0;
         __syncthreads();
     }
     // K6: 4-neighbour peaks above the accumulator threshold, interior cells only (x,y >= 1)
@@ -485,11 +491,21 @@ __global__ void __launch_bounds__(RW * 32) k_radius(const uint2 *__restrict__ ed
         for (int by = ylo / EB; by <= yhi / EB; by++)
             for (int bx = xlo / EB; bx <= xhi / EB; bx++) {
                 const int2 d = __ldg(mdir + by * nbx + bx);
-                for (int i = lane; i < d.y; i += 32) {
-                    const uint32_t e = __ldg(&elist[d.x + i].x);
-                    const int dxi = cx - (int)(e & 0xffff), dyi = cy - (int)(e >> 16);
-                    const int q = dxi * dxi + dxi + dyi * dyi + dyi;         // 1 <= r2 <= 900  <=>  1 <= q <= 899
-                    if ((unsigned)(q - 1) < 899u) atomicAdd(bins + s_binlut[q], 1);
+                // two list entries per lane and round: the loop is bound by the latency of its loads
+                for (int i = lane; i < d.y; i += 64) {
+                    const uint32_t e0 = __ldg(&elist[d.x + i].x);
+                    const bool two = i + 32 < d.y;
+                    const uint32_t e1 = two ? __ldg(&elist[d.x + i + 32].x) : 0u;
+                    {
+                        const int dxi = cx - (int)(e0 & 0xffff), dyi = cy - (int)(e0 >> 16);
+                        const int q = dxi * dxi + dxi + dyi * dyi + dyi;     // 1 <= r2 <= 900  <=>  1 <= q <= 899
+                        if ((unsigned)(q - 1) < 899u) atomicAdd(bins + s_binlut[q], 1);
+                    }
+                    if (two) {
+                        const int dxi = cx - (int)(e1 & 0xffff), dyi = cy - (int)(e1 >> 16);
+                        const int q = dxi * dxi + dxi + dyi * dyi + dyi;
+                        if ((unsigned)(q - 1) < 899u) atomicAdd(bins + s_binlut[q], 1);
+                    }
                 }
             }
         __syncwarp();

@@ -32,7 +32,7 @@ static uint32_t load_word(const uint8_t *row, int x, int w, bool reflect, int st
 
 extern "C" void rh_gauss357(const uint8_t *src, int h, int w, uint8_t *d3, uint8_t *d5, uint8_t *d7)
 {
-    const int TH = 64, OW = 120;
+    const int TH = 128, OW = 120;
     const int strips_x = (w + OW - 1) / OW, strips_y = (h + TH - 1) / TH;
     for (int sy = 0; sy < strips_y; sy++)
         for (int sx = 0; sx < strips_x; sx++) {
@@ -77,7 +77,7 @@ extern "C" void rh_gauss357(const uint8_t *src, int h, int w, uint8_t *d3, uint8
 // always_diag != 0 evaluates the diagonal test on every row (the kernel skips it per warp).
 extern "C" void rh_sobel_nms(const uint8_t *src, int ch, int h, int w, int low, int high, int always_diag, uint8_t *state)
 {
-    const int TH = 64, OW = 120;
+    const int TH = 128, OW = 120;
     const int strips_x = (w + OW - 1) / OW, strips_y = (h + TH - 1) / TH;
     const uint32_t l1 = (uint32_t)std::min(std::max(low + 1, 0), 0xffff), h1 = (uint32_t)std::min(std::max(high + 1, 0), 0xffff);
     const uint32_t low1 = l1 | (l1 << 16), high1 = h1 | (h1 << 16);

@@ -33,7 +33,7 @@ def _p(a):
 
 def _images(rng):
     out = []
-    for (h, w) in [(1, 1), (2, 3), (5, 4), (7, 129), (64, 120), (65, 121), (70, 250), (131, 37), (33, 480)]:
+    for (h, w) in [(1, 1), (2, 3), (5, 4), (7, 129), (64, 120), (65, 121), (70, 250), (131, 37), (33, 480), (300, 130), (257, 250)]:
         out.append(rng.integers(0, 256, (h, w), dtype=np.uint8))
     # smooth / tie-heavy content: quantised blobs and flat areas
     h, w = 150, 260
