@@ -38,7 +38,7 @@ if ROOT not in sys.path:
 
 WORKLOADS = {
     # name: (synth config, per-GPU batch, chunk)
-    "synth1024": ("synth1024", 1024, 128),
+    "synth1024": ("synth1024", 1024, 32),
     "synth2048": ("synth2048", 512, 16),
 }
 METRIC = "diagram images/sec"
@@ -400,7 +400,7 @@ def main():
     ap.add_argument("--workload", default="synth1024", choices=sorted(WORKLOADS))
     ap.add_argument("--per-gpu", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
-    ap.add_argument("--streams", type=int, default=2)
+    ap.add_argument("--streams", type=int, default=4)
     ap.add_argument("--cpu-images", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

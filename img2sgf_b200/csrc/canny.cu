@@ -253,9 +253,14 @@ __global__ void __launch_bounds__(CR_WARPS * 32, MINB) k_canny_roll(const MapSet
                     const int ny = py - 2;
                     const roll::MagRow &up = M[(u + 1) % 3], &c = M[(u + 2) % 3], &dn = M[u % 3];
                     const roll::Grad &g = G[(u + 1) % 2];
-                    roll::NmsPartial p = roll::nms_axis(up, c, dn, g, low1);
-                    if (__any_sync(0xffffffffu, roll::nms_needs_diag(p, c, low1))) roll::nms_diag(p, up, c, dn, g);
-                    const uint32_t st = roll::nms_state(p, c, high1);
+                    // rows without a single magnitude above `low` in the whole warp (blank paper, and most
+                    // of a median-filtered map, whose thin grid lines are gone) skip the NMS arithmetic
+                    uint32_t st = 0;
+                    if (__any_sync(0xffffffffu, roll::any_above(c, low1))) {
+                        roll::NmsPartial p = roll::nms_axis(up, c, dn, g, low1);
+                        if (__any_sync(0xffffffffu, roll::nms_needs_diag(p, c, low1))) roll::nms_diag(p, up, c, dn, g);
+                        st = roll::nms_state(p, c, high1);
+                    }
                     if (store_lane) {
                         const size_t o = (size_t)ny * w + x;
                         if (al) *reinterpret_cast<uint32_t *>(out + o) = st;
@@ -279,12 +284,11 @@ constexpr int HX = 16;                            // staged x halo: rows are 16-
 constexpr int HS_W = HT + 2 * HX, HS_H = HT + 2;  // y halo 1
 constexpr int HQ = (HT + 2) * (HT + 2);
 
-// One tile.  `tile` = (map * tiles_y + ty) * tiles_x + tx.  `phase` counts the uses of the block's
-// mbarrier (its parity is what a waiter passes).  Returns with all threads (uniform control flow).
+// One tile.  `tile` = (map * tiles_y + ty) * tiles_x + tx.  Returns with all threads (uniform control flow).
 __device__ __forceinline__ void hyst_tile(uint8_t *__restrict__ state, int h, int w, int tiles_x, int tiles_y,
                                           uint8_t *dirty_in, uint8_t *dirty_out, int pass, bool al, bool bulk,
                                           int tile, uint8_t *s_map, uint16_t *s_q, int &s_qn, int &s_changed,
-                                          int &s_ring, uint64_t &s_bar, uint32_t &phase)
+                                          int &s_ring, uint64_t &s_bar)
 {
     const int bx = tile % tiles_x, by = (tile / tiles_x) % tiles_y, bz = tile / (tiles_x * tiles_y);
     if (pass > 0) {
@@ -303,6 +307,8 @@ __device__ __forceinline__ void hyst_tile(uint8_t *__restrict__ state, int h, in
         const int cxa = max(x0 - HX, 0), cxb = min(x0 + HT + HX, w);
         const int ra = max(0, 1 - y0), rb = min(HS_H, h - y0 + 1);          // staged rows [ra, rb) lie in the image
         const int off = cxa - (x0 - HX);
+        if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
         if (threadIdx.x < 32) {
             if (threadIdx.x == 0) mbar_arrive_expect_tx(&s_bar, (uint32_t)((rb - ra) * (cxb - cxa)));
             for (int r = ra + threadIdx.x; r < rb; r += 32)
@@ -315,8 +321,7 @@ __device__ __forceinline__ void hyst_tile(uint8_t *__restrict__ state, int h, in
                 if (r < ra || r >= rb || c < wa || c >= wb) reinterpret_cast<uint32_t *>(s_map)[idx] = 0u;
             }
         }
-        mbar_wait(&s_bar, phase & 1u);
-        phase++;
+        mbar_wait(&s_bar, 0);
     } else {
         stage_tile_u8(s_map, HS_W, img, h, w, x0 - HX, y0 - 1, HS_W, HS_H, BORDER_ZERO, al);
     }
@@ -394,27 +399,20 @@ __device__ __forceinline__ void hyst_tile(uint8_t *__restrict__ state, int h, in
     }
 }
 
-// A block looks after `tiles_per_block` consecutive tiles (1 in production: several per block on the
-// later, mostly clean passes saves block launches but serialises the dirty tiles -- measured slower).
+// One block per tile.  (Several tiles per block on the later, mostly clean passes saves block
+// launches but serialises the dirty tiles, and any work ahead of the dirty check is paid by every
+// clean tile -- both measured slower.)
 __global__ void __launch_bounds__(256) k_hysteresis(uint8_t *__restrict__ state, int h, int w, int tiles_x,
-                                                    int tiles_y, int total_tiles, int tiles_per_block,
-                                                    uint8_t *dirty_in, uint8_t *dirty_out, int pass, bool al, bool bulk)
+                                                    int tiles_y, uint8_t *dirty_in, uint8_t *dirty_out, int pass,
+                                                    bool al, bool bulk)
 {
     extern __shared__ __align__(16) uint8_t s_dyn[];
     uint8_t *s_map = s_dyn;                                              // HS_H * HS_W bytes
     uint16_t *s_q = reinterpret_cast<uint16_t *>(s_dyn + HS_H * HS_W);   // HQ entries
     __shared__ int s_qn, s_changed, s_ring;
     __shared__ uint64_t s_bar;
-    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
-    __syncthreads();
-    uint32_t phase = 0;
-    for (int k = 0; k < tiles_per_block; k++) {
-        const int tile = blockIdx.x * tiles_per_block + k;
-        if (tile >= total_tiles) break;
-        hyst_tile(state, h, w, tiles_x, tiles_y, dirty_in, dirty_out, pass, al, bulk, tile, s_map, s_q, s_qn, s_changed,
-                  s_ring, s_bar, phase);
-        __syncthreads();                                                 // shared state is reused by the next tile
-    }
+    hyst_tile(state, h, w, tiles_x, tiles_y, dirty_in, dirty_out, pass, al, bulk, blockIdx.x, s_map, s_q, s_qn, s_changed,
+              s_ring, s_bar);
 }
 
 // after the last pass: any tile still dirty => that map did not converge
@@ -477,10 +475,7 @@ int canny_states(const MapSet &ms, int channels, uint8_t *state, int h, int w, i
             else
                 k_canny_roll<1, 6><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total);
         } else {
-            if (legacy_enabled("rgb5"))
-                k_canny_roll<3, 5><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total);
-            else
-                k_canny_roll<3, 4><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total);
+            k_canny_roll<3, 4><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total);
         }
     }
     I2S_CHECK_LAUNCH("k_sobel_nms");
@@ -508,9 +503,7 @@ int hysteresis(uint8_t *state, int maps, int n_images, int h, int w, int passes,
     }
     for (int p = 0; p < passes; p++) {
         uint8_t *din = (p & 1) ? d1 : d0, *dout = (p & 1) ? d0 : d1;
-        const int tpb = (p > 0 && legacy_enabled("hyst8")) ? 8 : 1;   // 8 tiles per block measured slower: dirty tiles then run one after another
-        k_hysteresis<<<(unsigned)((tiles + tpb - 1) / tpb), 256, kSmem, st>>>(state, h, w, tx, ty, (int)tiles, tpb, din, dout,
-                                                                             p, al, bulk);
+        k_hysteresis<<<(unsigned)tiles, 256, kSmem, st>>>(state, h, w, tx, ty, din, dout, p, al, bulk);
         I2S_CHECK_LAUNCH("k_hysteresis");
     }
     uint8_t *last = (passes & 1) ? d1 : d0;   // buffer written by the final pass

@@ -159,9 +159,9 @@ __global__ void __launch_bounds__(256) k_gauss357(const uint8_t *__restrict__ sr
 // fit), an exchange of the edge pairs with the neighbour lanes (8 shuffles) and the three
 // horizontal passes as 16-bit x 8-bit dot products (IDP.2A) into Q16, one rounding.  Lanes 0 and
 // 31 only supply the halo.  No shared memory, no barriers; arithmetic in roll_cores.cuh.
-constexpr int GR_TH = 128;         // output rows per warp strip (6 halo rows each)
+constexpr int GR_TH = 64;          // output rows per warp strip (128 rows / 4 warps measured slower)
 constexpr int GR_OW = 120;         // output columns per warp strip
-constexpr int GR_WARPS = 4;
+constexpr int GR_WARPS = 8;
 
 __device__ __forceinline__ uint32_t load_word_border(const uint8_t *__restrict__ row, int x, int w, bool al, int mode)
 {

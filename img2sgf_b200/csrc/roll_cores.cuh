@@ -227,6 +227,13 @@ I2S_HD void sector_masks(uint32_t ax, uint32_t ay, uint32_t &nh, uint32_t &v)
 // the caller then calls nms_diag() -- kept separate so a warp can skip it when no lane needs it.
 struct NmsPartial { uint32_t FA, FB, dA, dB; };   // fail values so far; diagonal-sector masks
 
+// some pixel of this lane has a magnitude above `low` (m >= low1)
+I2S_HD bool any_above(const MagRow &c, uint32_t low1)
+{
+    const uint32_t mx = max2(c.A, c.B);
+    return min2(max2(mx, low1) ^ mx, ONE2) != ONE2;
+}
+
 I2S_HD NmsPartial nms_axis(const MagRow &up, const MagRow &c, const MagRow &dn, const Grad &g, uint32_t low1)
 {
     uint32_t nhA, vA, nhB, vB;

@@ -32,7 +32,7 @@ static uint32_t load_word(const uint8_t *row, int x, int w, bool reflect, int st
 
 extern "C" void rh_gauss357(const uint8_t *src, int h, int w, uint8_t *d3, uint8_t *d5, uint8_t *d7)
 {
-    const int TH = 128, OW = 120;
+    const int TH = 64, OW = 120;
     const int strips_x = (w + OW - 1) / OW, strips_y = (h + TH - 1) / TH;
     for (int sy = 0; sy < strips_y; sy++)
         for (int sx = 0; sx < strips_x; sx++) {
@@ -133,6 +133,15 @@ extern "C" void rh_sobel_nms(const uint8_t *src, int ch, int h, int w, int low, 
                     if (it >= 4) {
                         const int ny = py - 2;
                         bool any = always_diag != 0;
+                        bool above = always_diag != 0;               // the kernel skips rows with no magnitude above low
+                        for (int lane = 0; lane < 32; lane++) above = above || any_above(M[lane][(u + 2) % 3], low1);
+                        if (!above) {
+                            for (int lane = 1; lane <= 30; lane++) {
+                                int x = sx * OW - 4 + 4 * lane;
+                                for (int k = 0; k < 4 && x + k < w && x < w; k++) state[(size_t)ny * w + x + k] = 0;
+                            }
+                            continue;
+                        }
                         NmsPartial P[32];
                         for (int lane = 0; lane < 32; lane++) {
                             P[lane] = nms_axis(M[lane][(u + 1) % 3], M[lane][(u + 2) % 3], M[lane][u % 3], G[lane][(u + 1) % 2], low1);
