@@ -156,7 +156,8 @@ __global__ void __launch_bounds__(256) k_sobel_nms(const MapSet ms, uint8_t *__r
 // instruction), two shuffles of the magnitudes and the branch-free packed NMS of the row two
 // above (roll_cores.cuh).  The diagonal-sector test runs only when some lane of the warp has a
 // diagonal candidate.  No shared memory, no barriers.
-constexpr int CR_TH = 128, CR_OW = 120, CR_WARPS = 4;   // 4 warm-up rows per 128-row strip
+constexpr int HT = 128;                           // hysteresis tile edge (see k_hysteresis)
+constexpr int CR_TH = HT, CR_OW = 120, CR_WARPS = 4;    // a strip spans exactly one row of hysteresis tiles
 
 template <int CH>
 __device__ __forceinline__ void canny_load(const uint8_t *__restrict__ row, int x, int w, bool al, uint32_t (&ch)[CH])
@@ -192,7 +193,7 @@ __device__ __forceinline__ void canny_load(const uint8_t *__restrict__ row, int 
 template <int CH, int MINB>
 __global__ void __launch_bounds__(CR_WARPS * 32, MINB) k_canny_roll(const MapSet ms, uint8_t *__restrict__ state, int h, int w,
                                                               uint32_t low1, uint32_t high1, bool al, int strips_x,
-                                                              int strips_y, int total)
+                                                              int strips_y, int total, uint8_t *__restrict__ tile_weak)
 {
     const int lane = threadIdx.x & 31;
     const int strip = blockIdx.x * CR_WARPS + (threadIdx.x >> 5);
@@ -210,6 +211,7 @@ __global__ void __launch_bounds__(CR_WARPS * 32, MINB) k_canny_roll(const MapSet
     roll::SobelRow R[3][CH];
     roll::MagRow M[3];
     roll::Grad G[2];
+    uint32_t weak_seen = 0;                                    // OR of "state byte == 1" over the rows stored
     const int iters = (y1 - y0) + 4;
     uint32_t nxt[CH];                                          // row loaded one iteration ahead of its use
     canny_load<CH>(img + (size_t)min(max(y0 - 2, 0), h - 1) * w * CH, x, w, al, nxt);
@@ -262,6 +264,7 @@ __global__ void __launch_bounds__(CR_WARPS * 32, MINB) k_canny_roll(const MapSet
                         st = roll::nms_state(p, c, high1);
                     }
                     if (store_lane) {
+                        weak_seen |= st & ~(st >> 1);
                         const size_t o = (size_t)ny * w + x;
                         if (al) *reinterpret_cast<uint32_t *>(out + o) = st;
                         else
@@ -271,6 +274,11 @@ __global__ void __launch_bounds__(CR_WARPS * 32, MINB) k_canny_roll(const MapSet
             }
         }
     }
+    // Hysteresis only has work where weak candidates exist: flag the 128x128 tile of this lane's pixels
+    // (a 4-pixel group never straddles a tile; the strip is one tile row).  k_hysteresis pass 0 visits
+    // flagged tiles only -- crisp diagrams have whole maps without a single weak pixel.
+    if (tile_weak && (weak_seen & 0x01010101u))
+        tile_weak[((size_t)map * strips_y + sy) * ((w + HT - 1) / HT) + (x / HT)] = 1;
 }
 
 // ------------------------------------------------------------------ hysteresis
@@ -279,19 +287,18 @@ __global__ void __launch_bounds__(CR_WARPS * 32, MINB) k_canny_roll(const MapSet
 // promotes candidates INSIDE the tile.  Each pixel enters the queue at most once, so the
 // queue never exceeds the staged area.  A tile whose outermost interior ring changed marks
 // its 8 neighbours dirty for the next pass; passes repeat until no tile is dirty.
-constexpr int HT = 128;
 constexpr int HX = 16;                            // staged x halo: rows are 16-byte aligned bulk copies
 constexpr int HS_W = HT + 2 * HX, HS_H = HT + 2;  // y halo 1
 constexpr int HQ = (HT + 2) * (HT + 2);
 
 // One tile.  `tile` = (map * tiles_y + ty) * tiles_x + tx.  Returns with all threads (uniform control flow).
 __device__ __forceinline__ void hyst_tile(uint8_t *__restrict__ state, int h, int w, int tiles_x, int tiles_y,
-                                          uint8_t *dirty_in, uint8_t *dirty_out, int pass, bool al, bool bulk,
+                                          uint8_t *dirty_in, uint8_t *dirty_out, int check_dirty, bool al, bool bulk,
                                           int tile, uint8_t *s_map, uint16_t *s_q, int &s_qn, int &s_changed,
                                           int &s_ring, uint64_t &s_bar)
 {
     const int bx = tile % tiles_x, by = (tile / tiles_x) % tiles_y, bz = tile / (tiles_x * tiles_y);
-    if (pass > 0) {
+    if (check_dirty) {
         const int d = dirty_in[tile];
         __syncthreads();                               // everyone has read the flag before it is cleared
         if (!d) return;
@@ -403,7 +410,7 @@ __device__ __forceinline__ void hyst_tile(uint8_t *__restrict__ state, int h, in
 // launches but serialises the dirty tiles, and any work ahead of the dirty check is paid by every
 // clean tile -- both measured slower.)
 __global__ void __launch_bounds__(256) k_hysteresis(uint8_t *__restrict__ state, int h, int w, int tiles_x,
-                                                    int tiles_y, uint8_t *dirty_in, uint8_t *dirty_out, int pass,
+                                                    int tiles_y, uint8_t *dirty_in, uint8_t *dirty_out, int check_dirty,
                                                     bool al, bool bulk)
 {
     extern __shared__ __align__(16) uint8_t s_dyn[];
@@ -411,7 +418,7 @@ __global__ void __launch_bounds__(256) k_hysteresis(uint8_t *__restrict__ state,
     uint16_t *s_q = reinterpret_cast<uint16_t *>(s_dyn + HS_H * HS_W);   // HQ entries
     __shared__ int s_qn, s_changed, s_ring;
     __shared__ uint64_t s_bar;
-    hyst_tile(state, h, w, tiles_x, tiles_y, dirty_in, dirty_out, pass, al, bulk, blockIdx.x, s_map, s_q, s_qn, s_changed,
+    hyst_tile(state, h, w, tiles_x, tiles_y, dirty_in, dirty_out, check_dirty, al, bulk, blockIdx.x, s_map, s_q, s_qn, s_changed,
               s_ring, s_bar);
 }
 
@@ -453,6 +460,9 @@ int canny_states(const MapSet &ms, int channels, uint8_t *state, int h, int w, i
 {
     const int maps = ms.count * ms.n;
     bool al = (w & 3) == 0 && ((uintptr_t)state & 3) == 0 && ms.aligned4();
+    const size_t tiles = (size_t)maps * cdiv(w, HT) * cdiv(h, HT);
+    uint8_t *flags = (uint8_t *)scratch;                       // = the first dirty buffer of hysteresis()
+    bool flagged = false;
     {
     ScopedSection sec(SEC_SOBEL_NMS, st);
     if (legacy_enabled("sobel")) {
@@ -468,23 +478,28 @@ int canny_states(const MapSet &ms, int channels, uint8_t *state, int h, int w, i
         // "m > low" as "m >= low + 1" on 16-bit halves; magnitudes never exceed 2040
         const uint32_t l1 = (uint32_t)min(max(low + 1, 0), 0xffff), h1 = (uint32_t)min(max(high + 1, 0), 0xffff);
         const uint32_t low1 = l1 | (l1 << 16), high1 = h1 | (h1 << 16);
+        flagged = !legacy_enabled("hystall");
+        if (flagged) I2S_CUDA(cudaMemsetAsync(flags, 0, align_up(tiles, 256) * 2, st));
+        uint8_t *tw = flagged ? flags : nullptr;
         if (channels == 1) {
-            // 6 resident blocks (80 registers, a few spilled words) against 5 (100 registers): A/B switch
+            // 6 resident blocks (80 registers, a few spilled words) against 5 (94 registers): A/B switch
             if (legacy_enabled("canny5"))
-                k_canny_roll<1, 5><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total);
+                k_canny_roll<1, 5><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total, tw);
             else
-                k_canny_roll<1, 6><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total);
+                k_canny_roll<1, 6><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total, tw);
         } else {
-            k_canny_roll<3, 4><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total);
+            k_canny_roll<3, 4><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total, tw);
         }
     }
     I2S_CHECK_LAUNCH("k_sobel_nms");
     }
-    return hysteresis(state, maps, ms.n, h, w, passes, status, scratch, st);
+    return hysteresis(state, maps, ms.n, h, w, passes, status, scratch, st, flagged);
 }
 
+// `tiles_flagged`: the first dirty buffer already holds the tiles pass 0 has to visit (written by
+// k_canny_roll: tiles with weak candidates); otherwise pass 0 visits every tile.
 int hysteresis(uint8_t *state, int maps, int n_images, int h, int w, int passes, int32_t *status,
-               void *scratch, cudaStream_t st)
+               void *scratch, cudaStream_t st, bool tiles_flagged)
 {
     bool al = (w & 3) == 0 && ((uintptr_t)state & 3) == 0;
     bool bulk = (w & 15) == 0 && ((uintptr_t)state & 15) == 0 && !legacy_enabled("hyst");
@@ -492,7 +507,7 @@ int hysteresis(uint8_t *state, int maps, int n_images, int h, int w, int passes,
     int tx = cdiv(w, HT), ty = cdiv(h, HT);
     size_t tiles = (size_t)maps * tx * ty;
     uint8_t *d0 = (uint8_t *)scratch, *d1 = d0 + align_up(tiles, 256);
-    I2S_CUDA(cudaMemsetAsync(d0, 0, align_up(tiles, 256) * 2, st));
+    if (!tiles_flagged) I2S_CUDA(cudaMemsetAsync(d0, 0, align_up(tiles, 256) * 2, st));
     if (passes < 1) passes = 1;
     I2S_ARG(tiles < (1ull << 31));
     constexpr int kSmem = HS_H * HS_W + HQ * 2;
@@ -503,7 +518,8 @@ int hysteresis(uint8_t *state, int maps, int n_images, int h, int w, int passes,
     }
     for (int p = 0; p < passes; p++) {
         uint8_t *din = (p & 1) ? d1 : d0, *dout = (p & 1) ? d0 : d1;
-        k_hysteresis<<<(unsigned)tiles, 256, kSmem, st>>>(state, h, w, tx, ty, din, dout, p, al, bulk);
+        k_hysteresis<<<(unsigned)tiles, 256, kSmem, st>>>(state, h, w, tx, ty, din, dout, (p > 0 || tiles_flagged) ? 1 : 0, al,
+                                                          bulk);
         I2S_CHECK_LAUNCH("k_hysteresis");
     }
     uint8_t *last = (passes & 1) ? d1 : d0;   // buffer written by the final pass
