@@ -295,7 +295,7 @@ constexpr int HQ = (HT + 2) * (HT + 2);
 __device__ __forceinline__ void hyst_tile(uint8_t *__restrict__ state, int h, int w, int tiles_x, int tiles_y,
                                           uint8_t *dirty_in, uint8_t *dirty_out, int check_dirty, bool al, bool bulk,
                                           int tile, uint8_t *s_map, uint16_t *s_q, int &s_qn, int &s_changed,
-                                          int &s_ring, uint64_t &s_bar)
+                                          int &s_ring, uint64_t &s_bar, uint32_t *phase)
 {
     const int bx = tile % tiles_x, by = (tile / tiles_x) % tiles_y, bz = tile / (tiles_x * tiles_y);
     if (check_dirty) {
@@ -314,8 +314,10 @@ __device__ __forceinline__ void hyst_tile(uint8_t *__restrict__ state, int h, in
         const int cxa = max(x0 - HX, 0), cxb = min(x0 + HT + HX, w);
         const int ra = max(0, 1 - y0), rb = min(HS_H, h - y0 + 1);          // staged rows [ra, rb) lie in the image
         const int off = cxa - (x0 - HX);
-        if (threadIdx.x == 0) mbar_init(&s_bar, 1);
-        __syncthreads();
+        if (!phase) {                                  // single-tile kernel: the barrier is used once
+            if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+            __syncthreads();
+        }
         if (threadIdx.x < 32) {
             if (threadIdx.x == 0) mbar_arrive_expect_tx(&s_bar, (uint32_t)((rb - ra) * (cxb - cxa)));
             for (int r = ra + threadIdx.x; r < rb; r += 32)
@@ -328,7 +330,8 @@ __device__ __forceinline__ void hyst_tile(uint8_t *__restrict__ state, int h, in
                 if (r < ra || r >= rb || c < wa || c >= wb) reinterpret_cast<uint32_t *>(s_map)[idx] = 0u;
             }
         }
-        mbar_wait(&s_bar, 0);
+        mbar_wait(&s_bar, phase ? (*phase & 1u) : 0u);
+        if (phase) ++*phase;
     } else {
         stage_tile_u8(s_map, HS_W, img, h, w, x0 - HX, y0 - 1, HS_W, HS_H, BORDER_ZERO, al);
     }
@@ -419,7 +422,48 @@ __global__ void __launch_bounds__(256) k_hysteresis(uint8_t *__restrict__ state,
     __shared__ int s_qn, s_changed, s_ring;
     __shared__ uint64_t s_bar;
     hyst_tile(state, h, w, tiles_x, tiles_y, dirty_in, dirty_out, check_dirty, al, bulk, blockIdx.x, s_map, s_q, s_qn, s_changed,
-              s_ring, s_bar);
+              s_ring, s_bar, nullptr);
+}
+
+// Sparse passes: k_hyst_list compacts the indices of the dirty tiles, k_hysteresis_list walks that
+// list with a grid sized for the machine, not for the tile count -- a pass over mostly clean maps
+// (the usual case after pass 0, and in pass 0 too for crisp diagrams) costs two small launches
+// instead of one block per tile.
+__global__ void __launch_bounds__(256) k_hyst_list(const uint8_t *__restrict__ dirty, int tiles, int *__restrict__ list,
+                                                   int *count)
+{
+    const int lane = threadIdx.x & 31;
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < tiles; base += gridDim.x * blockDim.x) {
+        const int t = base + lane;
+        const bool d = t < tiles && dirty[t];
+        const uint32_t m = __ballot_sync(0xffffffffu, d);
+        if (m == 0) continue;
+        int at = 0;
+        if (lane == 0) at = atomicAdd(count, __popc(m));
+        at = __shfl_sync(0xffffffffu, at, 0);
+        if (d) list[at + __popc(m & ((1u << lane) - 1u))] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_hysteresis_list(uint8_t *__restrict__ state, int h, int w, int tiles_x, int tiles_y,
+                                                         const int *__restrict__ list, const int *__restrict__ count,
+                                                         uint8_t *dirty_in, uint8_t *dirty_out, bool al, bool bulk)
+{
+    extern __shared__ __align__(16) uint8_t s_dyn[];
+    uint8_t *s_map = s_dyn;
+    uint16_t *s_q = reinterpret_cast<uint16_t *>(s_dyn + HS_H * HS_W);
+    __shared__ int s_qn, s_changed, s_ring;
+    __shared__ uint64_t s_bar;
+    const int n = *count;
+    if ((int)blockIdx.x >= n) return;
+    if (threadIdx.x == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    uint32_t phase = 0;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        hyst_tile(state, h, w, tiles_x, tiles_y, dirty_in, dirty_out, 1, al, bulk, list[i], s_map, s_q, s_qn, s_changed, s_ring,
+                  s_bar, &phase);
+        __syncthreads();                                   // shared state is reused by the next tile
+    }
 }
 
 // after the last pass: any tile still dirty => that map did not converge
@@ -448,10 +492,13 @@ __global__ void __launch_bounds__(256) k_state_to_edges4(const uint32_t *__restr
     }
 }
 
+constexpr int HYST_MAX_PASSES = 64;
+
 size_t canny_scratch_bytes(int maps, int h, int w)
 {
     size_t tiles = (size_t)maps * cdiv(w, HT) * cdiv(h, HT);
-    return align_up(tiles, 256) * 2 + 256;
+    // two dirty-flag buffers, the dirty-tile list, one list counter per pass
+    return align_up(tiles, 256) * 2 + align_up(tiles * sizeof(int), 256) + HYST_MAX_PASSES * sizeof(int) + 256;
 }
 
 // state: [ms.count * ms.n][h][w], map m = k * ms.n + i belongs to image i (for status)
@@ -516,10 +563,27 @@ int hysteresis(uint8_t *state, int maps, int n_images, int h, int w, int passes,
         I2S_CUDA(cudaFuncSetAttribute(k_hysteresis, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
         attr_done = true;
     }
+    int *list = (int *)(d1 + align_up(tiles, 256));
+    int *counts = (int *)((uint8_t *)list + align_up(tiles * sizeof(int), 256));
+    const bool sparse = !legacy_enabled("hystdense");
+    if (passes > HYST_MAX_PASSES) passes = HYST_MAX_PASSES;
+    if (sparse) I2S_CUDA(cudaMemsetAsync(counts, 0, HYST_MAX_PASSES * sizeof(int), st));
+    static bool attr2_done = false;
+    if (!attr2_done) {
+        I2S_CUDA(cudaFuncSetAttribute(k_hysteresis_list, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        attr2_done = true;
+    }
     for (int p = 0; p < passes; p++) {
         uint8_t *din = (p & 1) ? d1 : d0, *dout = (p & 1) ? d0 : d1;
-        k_hysteresis<<<(unsigned)tiles, 256, kSmem, st>>>(state, h, w, tx, ty, din, dout, (p > 0 || tiles_flagged) ? 1 : 0, al,
-                                                          bulk);
+        const bool check = p > 0 || tiles_flagged;
+        if (check && sparse) {
+            k_hyst_list<<<(unsigned)min((size_t)592, (tiles + 255) / 256), 256, 0, st>>>(din, (int)tiles, list, counts + p);
+            I2S_CHECK_LAUNCH("k_hyst_list");
+            k_hysteresis_list<<<(unsigned)min((size_t)(148 * 4), tiles), 256, kSmem, st>>>(state, h, w, tx, ty, list, counts + p,
+                                                                                            din, dout, al, bulk);
+        } else {
+            k_hysteresis<<<(unsigned)tiles, 256, kSmem, st>>>(state, h, w, tx, ty, din, dout, check ? 1 : 0, al, bulk);
+        }
         I2S_CHECK_LAUNCH("k_hysteresis");
     }
     uint8_t *last = (passes & 1) ? d1 : d0;   // buffer written by the final pass
