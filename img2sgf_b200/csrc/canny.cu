@@ -159,35 +159,41 @@ __global__ void __launch_bounds__(256) k_sobel_nms(const MapSet ms, uint8_t *__r
 constexpr int HT = 128;                           // hysteresis tile edge (see k_hysteresis)
 constexpr int CR_TH = HT, CR_OW = 120, CR_WARPS = 4;    // a strip spans exactly one row of hysteresis tiles
 
+// Raw words of one row for one lane: CH words holding the 4 pixels of this lane (CH = 3: the 12
+// interleaved RGB bytes).  Kept raw so that the row loaded one iteration ahead is not touched -- not
+// even by the de-interleaving permutes -- before the iteration that consumes it.
 template <int CH>
-__device__ __forceinline__ void canny_load(const uint8_t *__restrict__ row, int x, int w, bool al, uint32_t (&ch)[CH])
+__device__ __forceinline__ void canny_load(const uint8_t *__restrict__ row, int x, int w, bool al, uint32_t (&raw)[CH])
 {
-    if (CH == 1) {
-        if (al && x >= 0 && x + 3 < w) { ch[0] = __ldg(reinterpret_cast<const uint32_t *>(row + x)); return; }
-        if (x >= w + 8 || x < -8) { ch[0] = 0; return; }
-        uint32_t v = 0;
+    if (al && x >= 0 && x + 3 < w) {
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(row + (size_t)x * CH);
 #pragma unroll
-        for (int k = 0; k < 4; k++) v |= (uint32_t)__ldg(row + min(max(x + k, 0), w - 1)) << (8 * k);
-        ch[0] = v;
-    } else {
-        if (al && x >= 0 && x + 3 < w) {
-            const uint32_t *p = reinterpret_cast<const uint32_t *>(row + (size_t)x * 3);
-            const uint32_t w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
-            ch[0] = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);
-            ch[1 % CH] = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);
-            ch[2 % CH] = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);
-            return;
-        }
+        for (int c = 0; c < CH; c++) raw[c] = __ldg(p + c);
+        return;
+    }
 #pragma unroll
-        for (int c = 0; c < CH; c++) ch[c] = 0;
-        if (x >= w + 8 || x < -8) return;
+    for (int c = 0; c < CH; c++) raw[c] = 0;
+    if (x >= w + 8 || x < -8) return;                          // beyond any halo: value never used
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint8_t *p = row + (size_t)min(max(x + k, 0), w - 1) * CH;
+    for (int k = 0; k < 4; k++) {
+        const uint8_t *p = row + (size_t)min(max(x + k, 0), w - 1) * CH;
 #pragma unroll
-            for (int c = 0; c < CH; c++) ch[c] |= (uint32_t)__ldg(p + c) << (8 * k);
+        for (int c = 0; c < CH; c++) {
+            const int b = k * CH + c;                          // byte position inside the CH words
+            raw[b >> 2] |= (uint32_t)__ldg(p + c) << (8 * (b & 3));
         }
     }
+}
+
+// channel words (4 pixels of one channel each) from the raw words
+template <int CH>
+__device__ __forceinline__ void canny_channels(const uint32_t (&raw)[CH], uint32_t (&ch)[CH])
+{
+    if (CH == 1) { ch[0] = raw[0]; return; }
+    const uint32_t w0 = raw[0], w1 = raw[1 % CH], w2 = raw[2 % CH];
+    ch[0] = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);
+    ch[1 % CH] = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);
+    ch[2 % CH] = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);
 }
 
 template <int CH, int MINB>
@@ -224,8 +230,7 @@ __global__ void __launch_bounds__(CR_WARPS * 32, MINB) k_canny_roll(const MapSet
                 const int py = y0 - 2 + it;                    // pixel row consumed in this iteration
                 {
                     uint32_t ch[CH];
-#pragma unroll
-                    for (int c = 0; c < CH; c++) ch[c] = nxt[c];
+                    canny_channels<CH>(nxt, ch);
                     canny_load<CH>(img + (size_t)min(max(py + 1, 0), h - 1) * w * CH, x, w, al, nxt);
 #pragma unroll
                     for (int c = 0; c < CH; c++) {
@@ -529,11 +534,11 @@ int canny_states(const MapSet &ms, int channels, uint8_t *state, int h, int w, i
         if (flagged) I2S_CUDA(cudaMemsetAsync(flags, 0, align_up(tiles, 256) * 2, st));
         uint8_t *tw = flagged ? flags : nullptr;
         if (channels == 1) {
-            // 6 resident blocks (80 registers, a few spilled words) against 5 (94 registers): A/B switch
-            if (legacy_enabled("canny5"))
-                k_canny_roll<1, 5><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total, tw);
-            else
+            // 5 resident blocks (no spills) measured 2 % faster than 6 (80 registers, a few spilled words)
+            if (legacy_enabled("canny6"))
                 k_canny_roll<1, 6><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total, tw);
+            else
+                k_canny_roll<1, 5><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total, tw);
         } else {
             k_canny_roll<3, 4><<<blocks, CR_WARPS * 32, 0, st>>>(ms, state, h, w, low1, high1, al, strips_x, strips_y, (int)total, tw);
         }

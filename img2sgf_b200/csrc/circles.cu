@@ -563,6 +563,150 @@ __global__ void __launch_bounds__(RW * 32) k_radius(const uint2 *__restrict__ ed
     }
 }
 
+// ---- second generation: four centres per warp ---------------------------------------------------
+// The scan over the 290 bins is sequential and identical in every lane, so a whole warp per centre
+// spends most of its instructions 32-fold redundantly.  Here 8 lanes share a centre (4 centres per
+// warp): the histogram loop keeps its per-lane throughput, the prefix / bitmap / scan phases are
+// paid once per 4 centres.  Bins and prefix sums are 16-bit (at most 61*61 pixels lie within
+// 30 px), two bins per 32-bit atomic word.
+constexpr int RG = 8;                       // lanes per centre
+constexpr int RCW = 32 / RG;                // centres per warp
+constexpr int RW4 = 4;                      // warps per block
+constexpr int RBL = RBINS / RG;             // bins per lane in the prefix pass (40)
+
+__global__ void __launch_bounds__(RW4 * 32) k_radius4(const uint2 *__restrict__ edges, const int2 *__restrict__ dir,
+                                                     int nbx, int nby, int h, int w,
+                                                     const int32_t *__restrict__ cand, const int32_t *__restrict__ ncand,
+                                                     int cand_cap, unsigned long long *est, int32_t *nest, int32_t *status,
+                                                     int n_images)
+{
+    __shared__ uint32_t s_bins[RW4 * RCW][RBINS / 2];          // two 16-bit bins per word
+    __shared__ uint16_t s_pref[RW4 * RCW][RBINS];
+    __shared__ uint32_t s_mask[RW4 * RCW][RBINS / 32];
+    __shared__ float s_rtab[RQ];
+    __shared__ uint16_t s_binlut[900];
+    const int map = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane / RG, gl = lane % RG;                 // centre slot inside the warp, lane inside the group
+    const uint2 *elist = edges + (size_t)map * h * w;
+    const int2 *mdir = dir + (size_t)map * nbx * nby;
+    const int aw = w + 2;
+    int n = ncand[map];
+    if (n > cand_cap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(status + map % n_images, I2S_ST_CAND_OVERFLOW);
+        n = cand_cap;
+    }
+    if ((int)blockIdx.x * RW4 * RCW >= n) return;
+    for (int q = threadIdx.x; q < RQ; q += blockDim.x) s_rtab[q] = radius_of_q(q);
+    for (int q = threadIdx.x; q < 900; q += blockDim.x) {      // exact bin table, see k_radius
+        const float dd = __fsqrt_rn((float)q + 0.5f);
+        const int bin = __float2int_rn(__fmul_rn(__fsub_rn(dd, 1.0f), 10.0f));
+        s_binlut[q] = (uint16_t)min(max(bin, 0), NBINS - 1);
+    }
+    __syncthreads();
+    uint32_t *bins = s_bins[warp * RCW + grp];
+    uint16_t *pref = s_pref[warp * RCW + grp];
+    uint32_t *mask = s_mask[warp * RCW + grp];
+    const uint16_t *bins16 = reinterpret_cast<const uint16_t *>(bins);
+    for (int c0 = (blockIdx.x * RW4 + warp) * RCW; c0 < n; c0 += gridDim.x * RW4 * RCW) {      // warp-uniform
+        const int c = c0 + grp;
+        const bool live = c < n;
+        int cx = 0, cy = 0;
+        if (live) {
+            const int base = cand[(size_t)map * cand_cap + c];
+            cy = base / aw; cx = base - cy * aw;
+        }
+        for (int b = gl; b < RBINS / 2; b += RG) bins[b] = 0;
+        if (gl < RBINS / 32) mask[gl] = 0;
+        if (gl + RG < RBINS / 32) mask[gl + RG] = 0;
+        __syncwarp();
+        if (live) {
+            const int xlo = max(cx - 29, 0), xhi = min(cx + 30, w - 1);
+            const int ylo = max(cy - 29, 0), yhi = min(cy + 30, h - 1);
+            for (int by = ylo / EB; by <= yhi / EB; by++)
+                for (int bx = xlo / EB; bx <= xhi / EB; bx++) {
+                    const int2 d = __ldg(mdir + by * nbx + bx);
+                    // four list entries per lane and round: the loop is bound by the latency of its loads
+                    for (int i = gl; i < d.y; i += 4 * RG) {
+                        uint32_t e[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) e[u] = (i + u * RG < d.y) ? __ldg(&elist[d.x + i + u * RG].x) : 0u;
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int dxi = cx - (int)(e[u] & 0xffff), dyi = cy - (int)(e[u] >> 16);
+                            const int q = dxi * dxi + dxi + dyi * dyi + dyi;     // 1 <= r2 <= 900  <=>  1 <= q <= 899
+                            if (i + u * RG < d.y && (unsigned)(q - 1) < 899u) {
+                                const int b = s_binlut[q];
+                                atomicAdd(bins + (b >> 1), (b & 1) ? 0x10000u : 1u);
+                            }
+                        }
+                    }
+                }
+        }
+        __syncwarp();
+        // inclusive prefix sums (RBL consecutive bins per lane, group scan over RG lanes) and the
+        // non-zero bitmap (bits OR-ed into the shared words a lane's bins fall in)
+        {
+            int sum = 0;
+            for (int k = 0; k < RBL / 2; k++) {
+                const uint32_t v = bins[gl * (RBL / 2) + k];
+                sum += (int)(v & 0xffffu) + (int)(v >> 16);
+            }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < RG; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o, RG);
+                if (gl >= o) incl += t;
+            }
+            int run = incl - sum;
+            uint32_t bits = 0;
+            int word = (gl * RBL) >> 5;
+            for (int k = 0; k < RBL; k++) {
+                const int b = gl * RBL + k;
+                if ((b >> 5) != word) {
+                    if (bits) atomicOr(mask + word, bits);
+                    bits = 0; word = b >> 5;
+                }
+                const int v = bins16[b];
+                run += v;
+                pref[b] = (uint16_t)run;
+                if (v) bits |= 1u << (b & 31);
+            }
+            if (bits) atomicOr(mask + word, bits);
+        }
+        __syncwarp();
+        // OpenCV's scan from the top bin, uniform across the lanes of a group
+        int maxCount = 0, bestq = 0;
+        float rBest = 0.0f;
+        int j = NBINS - 1;
+        while (j > 0) {
+            int wd = j >> 5;
+            uint32_t m = mask[wd] & (0xffffffffu >> (31 - (j & 31)));
+            while (m == 0 && --wd >= 0) m = mask[wd];
+            if (m == 0) break;
+            int up = wd * 32 + 31 - __clz(m);
+            if (up <= 0) break;
+            int jn = up - 10, cur;
+            if (jn >= 0) cur = (int)pref[up] - (int)pref[jn];
+            else { cur = pref[up]; jn = -1; }
+            float rCur = s_rtab[up + jn];
+            if ((__fmul_rn((float)cur, rBest) >= __fmul_rn((float)maxCount, rCur)) ||
+                (rBest < 1.1920929e-07f && cur >= maxCount)) {
+                rBest = rCur; maxCount = cur; bestq = up + jn;
+            }
+            j = jn - 1;
+        }
+        if (live && gl == 0 && maxCount > ACC_THR) {
+            int slot = atomicAdd(nest + map, 1);
+            if (slot < cand_cap)
+                est[(size_t)map * cand_cap + slot] = ((unsigned long long)(4095 - maxCount) << 38) |
+                                                     ((unsigned long long)(1023 - bestq) << 28) |
+                                                     ((unsigned long long)cx << 14) | (unsigned long long)cy;
+        }
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------ K7b: total-order sort + greedy minDist
 // One block per map: bitonic sort of the packed keys (support desc, radius desc, x asc, y asc),
 // then warp 0 runs the sequential suppression (kept iff >= 10 px from every kept circle).  Kept
@@ -800,7 +944,10 @@ int hough_circles_maps(const MapSet &ms, int h, int w, float *mcirc, int32_t *mc
     }
     {
         ScopedSection sec(SEC_RADIUS, st);
-        k_radius<<<dim3(16, maps), RW * 32, 0, st>>>(edges, dir, nbx, nby, h, w, cand, ncand, lim.cand_cap, est, nest, status, ms.n);
+        if (legacy_enabled("radius"))
+            k_radius<<<dim3(16, maps), RW * 32, 0, st>>>(edges, dir, nbx, nby, h, w, cand, ncand, lim.cand_cap, est, nest, status, ms.n);
+        else
+            k_radius4<<<dim3(16, maps), RW4 * 32, 0, st>>>(edges, dir, nbx, nby, h, w, cand, ncand, lim.cand_cap, est, nest, status, ms.n);
         I2S_CHECK_LAUNCH("k_radius");
     }
     ScopedSection sec(SEC_CIRCLES_FINISH, st);
