@@ -8,13 +8,16 @@ roofline and the reference CPU path timed beside it.
 Workload (BASELINE.json configs[3]): synthetic 1024x1024 diagrams (s=50, r=24, line threshold
 pinned to 150), 1024 images per GPU (8192 over 8 GPUs), the whole path
 RGB array -> 19x19 board record, weak scaling over image shards with one NCCL all-gather of
-the 384-byte records.  A "step" is one pass of the path over the rank's whole batch.
+the 384-byte records.  A "step" is one pass of the path over the rank's whole batch, in chunks
+of 32 images alternating between 4 CUDA streams.
 
 `value`  : images/s with the inputs already resident in HBM (CUDA events, max over ranks).
 `e2e`    : the same through the public API with HOST (pinned) buffers: H2D of every image and
            D2H of the records inside the timed region.
-`roofline`: Hough accumulator kernels (k_edge_buckets + k_vote_peaks), algorithmic bytes
-           10*W*H per HoughCircles call over their CUDA-event time inside the step.
+`roofline`: Hough accumulator kernels (k_edge_buckets16 + k_vote_peaks2), algorithmic bytes
+           10*W*H per HoughCircles call over their CUDA-event time, taken in a
+           second pass of the same K steps on ONE stream (`sections_pass`).
+`roofline_config2`: the same measurement on BASELINE.json configs[2] (2048x2048 diagrams), N=1 only.
 `cpu_baseline`: the reference's own cv2/sklearn calls (oracle/ref_replay.py) on all host cores,
            one process per core, on a bounded sample of the same workload.
 """
@@ -217,6 +220,11 @@ def run_ours(args, rank, world, local_rank):
                "sample": f"{n} images of the workload, one single-threaded process per core, {dt:.1f} s wall "
                          f"(cv2 {_cv2_version()})"}
     grey, truth = generate(config, rank * per_gpu, per_gpu, max(1, min(32, cores // max(world, 1))))
+    # BASELINE.json configs[2] ("synthetic 2048x2048 ... 1 GPU HBM-roofline run"): a second, short
+    # Hough-accum roofline measurement on 2048^2 diagrams next to the default workload's (N=1 only)
+    grey2k = None
+    if world == 1 and args.workload == "synth1024" and not args.no_roofline2048:
+        grey2k, _ = generate("synth2048", 0, args.images2048, max(1, min(32, cores)))
 
     import torch
     import torch.distributed as dist
@@ -287,6 +295,37 @@ def run_ours(args, rank, world, local_rank):
     N.check(lib.i2s_profile_read(ms, cnt, nsec), "i2s_profile_read")
     lib.i2s_profile_enable(0)
     prof_ms_per_step = p0.elapsed_time(p1) / args.steps
+
+    roof2k = None
+    if grey2k is not None:
+        size2, _, _, thr2 = synth.CONFIGS["synth2048"]
+        n2, chunk2 = grey2k.shape[0], WORKLOADS["synth2048"][2]
+        dev2 = torch.from_numpy(grey2k)[..., None].expand(-1, -1, -1, 3).contiguous().cuda()
+        run2 = B.BatchRunner(size2, size2, chunk2, streams=1)
+        rec2 = torch.zeros((n2, B.RECORD_BYTES), dtype=torch.uint8, device="cuda")
+        for _ in range(2):
+            run2.run(dev2, thr2, 128, records=rec2)
+        torch.cuda.synchronize()
+        lib.i2s_profile_enable(1)
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for _ in range(args.steps):
+            run2.run(dev2, thr2, 128, records=rec2)
+        q1.record()
+        torch.cuda.synchronize()
+        ms2 = (C.c_double * nsec)(); cnt2 = (C.c_longlong * nsec)()
+        N.check(lib.i2s_profile_read(ms2, cnt2, nsec), "i2s_profile_read")
+        lib.i2s_profile_enable(0)
+        names = [lib.i2s_profile_section_name(i).decode() for i in range(nsec)]
+        acc2 = sum(ms2[i] for i in range(nsec) if names[i] in ("edge_list", "vote")) / args.steps
+        bad2 = int((B.records_to_numpy(rec2)["status"] != 0).sum())
+        alg2 = 10.0 * size2 * size2 * 8 * n2
+        roof2k = {"workload": f"synth2048: {size2}x{size2} synthetic diagrams (BASELINE.json configs[2]), {n2} images, "
+                              f"chunk {chunk2}, one stream, full path", "images_per_s": n2 * args.steps / (q0.elapsed_time(q1) / 1000.0),
+                  "bound": "hbm", "achieved": alg2 / (acc2 / 1000.0) / 1e9, "unit": "GB/s",
+                  "algorithmic_bytes_per_call": 10 * size2 * size2, "ms_per_step": acc2, "bad_status": bad2}
+        del dev2, run2, rec2
+        torch.cuda.empty_cache()
 
     # ---- end to end: pinned host RGB in, host records out, every step
     e2e = None
@@ -380,6 +419,7 @@ def run_ours(args, rank, world, local_rank):
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                          "algorithmic_bytes_per_call": 10 * size * size, "ms_per_step": acc_ms,
                          "share_of_step": acc_ms / prof_ms_per_step},
+            "roofline_config2": (dict(roof2k, peak=peak, frac=roof2k["achieved"] / peak) if roof2k else None),
             "cpu_baseline": cpu,
             "sections": sections,
             "sections_pass": {"streams": 1, "ms_per_step": prof_ms_per_step,
@@ -404,6 +444,8 @@ def main():
     ap.add_argument("--cpu-images", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-roofline2048", action="store_true")
+    ap.add_argument("--images2048", type=int, default=64)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

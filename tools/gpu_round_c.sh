@@ -11,7 +11,7 @@ if [ $rc -ne 0 ]; then
     I2S_LEGACY=$leg timeout 600 $T -x > gpurun_out/pytest_${TAG}_$leg.log 2>&1; echo "legacy=$leg rc=$?"; tail -1 gpurun_out/pytest_${TAG}_$leg.log
   done
 fi
-B="python bench.py --per-gpu 512 --steps 2 --warmup 2 --no-cpu-baseline --no-e2e"
+B="python bench.py --per-gpu 512 --steps 2 --warmup 2 --no-cpu-baseline --no-e2e --no-roofline2048"
 for leg in $VARIANTS; do
   I2S_LEGACY=$leg timeout 600 $B > gpurun_out/bench_${TAG}_$leg.json 2> gpurun_out/bench_${TAG}_$leg.err
   python - <<PY
