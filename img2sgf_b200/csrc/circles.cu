@@ -140,21 +140,16 @@ __global__ void __launch_bounds__(256) k_edge_buckets(const MapSet ms, const uin
     edge_emit(img, h, w, map, plane, s_pos, s_n, s_off, s_end, edges, ecount, dir, nbx, nby);
 }
 
-// Same list with 16 pixels (one 128-bit load) per thread, and ordered one level finer: thread t owns
-// row t/4 and the 16-pixel column group t%4 of the block's 64x64 pixels, i.e. one row of one 16x16
-// SUB-bucket; the lanes of a warp with the same t%4 share a sub-bucket (8 rows of it) and need one
-// 5-bit ballot prefix per 16 pixels.  Inside a 32x32 bucket the four sub-buckets are stored one after
-// the other, so the bucket directory `dir` is unchanged (k_vote_peaks2 walks whole buckets) while
-// `dir16` lets k_radius visit only the 16x16 cells its 60x60 window touches.
-// Requires w % 16 == 0 and a 16-byte aligned state map.
-constexpr int SB = 16;
-
+// Same result with 16 pixels (one 128-bit load) per thread: thread t owns row t/4 and the 16-pixel
+// column group t%4 of the block's 64x64 pixels, so a warp covers 8 rows of two buckets (lanes with
+// the same bit 1 share a bucket) and needs one 5-bit ballot prefix per 16 pixels instead of one
+// 3-bit prefix per 4.  Requires w % 16 == 0 and a 16-byte aligned state map.
 __global__ void __launch_bounds__(256) k_edge_buckets16(const MapSet ms, const uint8_t *__restrict__ state, int h, int w,
-                                                        uint2 *__restrict__ edges, int32_t *ecount, int2 *dir, int2 *dir16,
-                                                        int nbx, int nby, int nbx16, int nby16)
+                                                        uint2 *__restrict__ edges, int32_t *ecount, int2 *dir,
+                                                        int nbx, int nby)
 {
-    __shared__ uint32_t s_pos[16][SB * SB];
-    __shared__ int s_n[16], s_off[16], s_end[17];
+    __shared__ uint32_t s_pos[4][EB * EB];
+    __shared__ int s_n[4], s_off[4], s_end[5];
     const size_t plane = (size_t)h * w;
     const int map = blockIdx.z;
     const uint8_t *img = ms.plane(map, plane);
@@ -162,14 +157,14 @@ __global__ void __launch_bounds__(256) k_edge_buckets16(const MapSet ms, const u
     const int lane = threadIdx.x & 31;
     const int row = threadIdx.x >> 2, cg = threadIdx.x & 3;
     const int y = blockIdx.y * (2 * EB) + row, x = blockIdx.x * (2 * EB) + cg * 16;
-    const int sub = (row >> 4) * 4 + cg;                       // sub-bucket (row / 16, cg) of the block
-    if (threadIdx.x < 16) s_n[threadIdx.x] = 0;
+    const int sub = (row >> 5) * 2 + (cg >> 1);
+    if (threadIdx.x < 4) s_n[threadIdx.x] = 0;
     __syncthreads();
     uint4 v = make_uint4(0, 0, 0, 0);
     if (y < h && x < w) v = __ldg(reinterpret_cast<const uint4 *>(stm + (size_t)y * w + x));
     uint32_t wd[4] = {v.x & 0x02020202u, v.y & 0x02020202u, v.z & 0x02020202u, v.w & 0x02020202u};
     const int nbits = __popc(wd[0]) + __popc(wd[1]) + __popc(wd[2]) + __popc(wd[3]);      // 0..16
-    const uint32_t bm = 0x11111111u << cg;                                                 // lanes of my sub-bucket
+    const uint32_t bm = (lane & 2) ? 0xccccccccu : 0x33333333u;                            // lanes of my bucket
     const uint32_t lt = ((1u << lane) - 1u) & bm;
     int pre = 0, tot = 0;
 #pragma unroll
@@ -179,8 +174,8 @@ __global__ void __launch_bounds__(256) k_edge_buckets16(const MapSet ms, const u
         tot += __popc(b & bm) << k;
     }
     int base = 0;
-    if (lane < 4 && tot) base = atomicAdd(&s_n[sub], tot);     // lanes 0..3 are the first lanes of the four groups
-    base = __shfl_sync(0xffffffffu, base, lane & 3);
+    if ((lane == 0 || lane == 2) && tot) base = atomicAdd(&s_n[sub], tot);
+    base = __shfl_sync(0xffffffffu, base, lane & 2);
     int pos = base + pre;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -191,57 +186,7 @@ __global__ void __launch_bounds__(256) k_edge_buckets16(const MapSet ms, const u
             s_pos[sub][pos++] = ((uint32_t)y << 16) | (uint32_t)(x + 4 * k + j);
         }
     }
-    __syncthreads();
-    if (threadIdx.x < 4) {                                     // one thread per 32x32 bucket of the block
-        const int b32 = threadIdx.x;
-        const int bxx = blockIdx.x * 2 + (b32 & 1), byy = blockIdx.y * 2 + (b32 >> 1);
-        int subs[4], n32 = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            subs[k] = ((b32 >> 1) * 2 + (k >> 1)) * 4 + (b32 & 1) * 2 + (k & 1);
-            n32 += s_n[subs[k]];
-        }
-        int off = 0;
-        if (bxx < nbx && byy < nby) {
-            off = n32 ? atomicAdd(ecount + map, n32) : 0;
-            dir[((size_t)map * nby + byy) * nbx + bxx] = make_int2(off, n32);
-        }
-        int run = off;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int sy = subs[k] >> 2, sx = subs[k] & 3;
-            const int bx16 = blockIdx.x * 4 + sx, by16 = blockIdx.y * 4 + sy;
-            s_off[subs[k]] = run;
-            if (bx16 < nbx16 && by16 < nby16) dir16[((size_t)map * nby16 + by16) * nbx16 + bx16] = make_int2(run, s_n[subs[k]]);
-            run += s_n[subs[k]];
-        }
-    }
-    if (threadIdx.x == 32) {
-        s_end[0] = 0;
-        for (int k = 0; k < 16; k++) s_end[k + 1] = s_end[k] + s_n[k];
-    }
-    __syncthreads();
-    uint2 *out = edges + (size_t)map * plane;
-    const int total = s_end[16];
-    int sb = 0;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        while (i >= s_end[sb + 1]) sb++;
-        const int li = i - s_end[sb];
-        const uint32_t e = s_pos[sb][li];
-        const int ex = e & 0xffff, ey = e >> 16;
-        int dx, dy;
-        sobel_at(img, h, w, ex, ey, dx, dy);
-        int sx = 0, sy = 0;
-        if (dx != 0 || dy != 0) {
-            float vx = (float)dx, vy = (float)dy;
-            float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)));
-            if (!(mag < 1.0f)) {
-                sx = __float2int_rn(__fdiv_rn(__fmul_rn(vx, 1024.0f), mag));
-                sy = __float2int_rn(__fdiv_rn(__fmul_rn(vy, 1024.0f), mag));
-            }
-        }
-        out[s_off[sb] + li] = make_uint2(e, (uint32_t)(sx & 0xffff) | ((uint32_t)sy << 16));   // (0,0) step = no vote
-    }
+    edge_emit(img, h, w, map, plane, s_pos, s_n, s_off, s_end, edges, ecount, dir, nbx, nby);
 }
 
 // ------------------------------------------------------------------ K5+K6: voting fused with peak finding
@@ -501,7 +446,7 @@ constexpr int RBINS = 320;     // NBINS padded to a multiple of 32 (pad stays ze
 constexpr int RQ = 576;        // radius table size: q = upbin + j <= 289 + 279
 
 __global__ void __launch_bounds__(RW * 32) k_radius(const uint2 *__restrict__ edges, const int2 *__restrict__ dir,
-                                                   int nbx, int nby, int gshift, int h, int w,
+                                                   int nbx, int nby, int h, int w,
                                                    const int32_t *__restrict__ cand, const int32_t *__restrict__ ncand,
                                                    int cand_cap, unsigned long long *est, int32_t *nest, int32_t *status,
                                                    int n_images)
@@ -539,13 +484,13 @@ __global__ void __launch_bounds__(RW * 32) k_radius(const uint2 *__restrict__ ed
         int cy = base / aw, cx = base - cy * aw;
         for (int b = lane; b < RBINS; b += 32) bins[b] = 0;
         __syncwarp();
-        // histogram of the distances to the edge pixels within 30 px: walk the cells of the edge-list
-        // directory (`dir`, `nbx` x `nby` cells of 1 << gshift pixels: 16x16 sub-buckets when the list
-        // has them, else the 32x32 buckets) that overlap the 60x60 window
+        // histogram of the distances to the edge pixels within 30 px: walk the edge-list buckets
+        // that overlap the 60x60 window (at most 3x3 of them).  (A finer 16x16 directory was tried:
+        // fewer entries to reject, but cells of ~18 entries leave half a warp idle -- slower.)
         const int xlo = max(cx - 29, 0), xhi = min(cx + 30, w - 1);
         const int ylo = max(cy - 29, 0), yhi = min(cy + 30, h - 1);
-        for (int by = ylo >> gshift; by <= yhi >> gshift; by++)
-            for (int bx = xlo >> gshift; bx <= xhi >> gshift; bx++) {
+        for (int by = ylo / EB; by <= yhi / EB; by++)
+            for (int bx = xlo / EB; bx <= xhi / EB; bx++) {
                 const int2 d = __ldg(mdir + by * nbx + bx);
                 // two list entries per lane and round: the loop is bound by the latency of its loads
                 for (int i = lane; i < d.y; i += 64) {
@@ -808,7 +753,6 @@ size_t circles_scratch_bytes(int maps, int h, int w, const i2s_limits_t &lim)
     b += align_up(maps * plane, 256);                               // state maps
     b += align_up(maps * plane * 8, 256);                           // edge lists (position, Q10 step), worst case
     b += align_up((size_t)maps * cdiv(w, EB) * cdiv(h, EB) * 8, 256);   // bucket directory
-    b += align_up((size_t)maps * cdiv(w, SB) * cdiv(h, SB) * 8, 256);   // sub-bucket directory
     b += align_up((size_t)maps * lim.cand_cap * 4, 256);            // candidate centres
     b += align_up((size_t)maps * lim.cand_cap * 8, 256);            // estimated circle keys
     b += align_up((size_t)maps * 4 * 4, 256);                       // counters
@@ -827,8 +771,6 @@ int hough_circles_maps(const MapSet &ms, int h, int w, float *mcirc, int32_t *mc
     uint2 *edges = ar.take<uint2>(maps * plane);
     const int nbx = cdiv(w, EB), nby = cdiv(h, EB);
     int2 *dir = ar.take<int2>((size_t)maps * nbx * nby);
-    const int nbx16 = cdiv(w, SB), nby16 = cdiv(h, SB);
-    int2 *dir16 = ar.take<int2>((size_t)maps * nbx16 * nby16);
     int32_t *cand = ar.take<int32_t>((size_t)maps * lim.cand_cap);
     unsigned long long *est = ar.take<unsigned long long>((size_t)maps * lim.cand_cap);
     int32_t *ctr = ar.take<int32_t>((size_t)maps * 3);
@@ -845,7 +787,7 @@ int hough_circles_maps(const MapSet &ms, int h, int w, float *mcirc, int32_t *mc
         ScopedSection sec(SEC_EDGE_LIST, st);
         const dim3 eg(cdiv(nbx, 2), cdiv(nby, 2), maps);
         if (fine)
-            k_edge_buckets16<<<eg, 256, 0, st>>>(ms, state, h, w, edges, ecount, dir, dir16, nbx, nby, nbx16, nby16);
+            k_edge_buckets16<<<eg, 256, 0, st>>>(ms, state, h, w, edges, ecount, dir, nbx, nby);
         else
             k_edge_buckets<<<eg, 256, 0, st>>>(ms, state, h, w, al, edges, ecount, dir, nbx, nby);
         I2S_CHECK_LAUNCH("k_edge_buckets");
@@ -862,10 +804,7 @@ int hough_circles_maps(const MapSet &ms, int h, int w, float *mcirc, int32_t *mc
         ScopedSection sec(SEC_RADIUS, st);
         // (a variant with four centres per warp -- 8 lanes each, 16-bit bins -- cut the instruction count by
         // 18 % but not the time: the loop over the bucket entries dominates, not the per-centre scan)
-        if (fine && !legacy_enabled("radius32"))
-            k_radius<<<dim3(16, maps), RW * 32, 0, st>>>(edges, dir16, nbx16, nby16, 4, h, w, cand, ncand, lim.cand_cap, est, nest, status, ms.n);
-        else
-            k_radius<<<dim3(16, maps), RW * 32, 0, st>>>(edges, dir, nbx, nby, 5, h, w, cand, ncand, lim.cand_cap, est, nest, status, ms.n);
+        k_radius<<<dim3(16, maps), RW * 32, 0, st>>>(edges, dir, nbx, nby, h, w, cand, ncand, lim.cand_cap, est, nest, status, ms.n);
         I2S_CHECK_LAUNCH("k_radius");
     }
     ScopedSection sec(SEC_CIRCLES_FINISH, st);
