@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: gpu_round_c.sh "<legacy variants>" "<ncu kernel regex>"   (A/B pass, CSV export on the box)
+# usage: gpu_ab.sh "<legacy variants>" "<ncu kernel regex>"   (A/B pass, CSV export on the box)
 mkdir -p gpurun_out; rm -f gpurun_out/*.ncu-rep
 VARIANTS=${1:-"none"}; KREGEX=${2:-""}; TAG=${3:-c}
 T="python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider"
