@@ -313,6 +313,7 @@ __global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks(const uint2 *__rest
 // iteration after one binary search per warp, consecutive lanes hold consecutive contour pixels
 // (similar ray lengths, neighbouring banks), and the peak scan reads rows with lane-consecutive
 // columns, testing the threshold before anything else.
+template <int UNROLL>
 __device__ __forceinline__ void vote_item(int *s_acc, uint2 e, int cx0, int cy0, int X0, int X1, int Y0, int Y1)
 {
     const int x = e.x & 0xffff, y = e.x >> 16;
@@ -336,11 +337,12 @@ __device__ __forceinline__ void vote_item(int *s_acc, uint2 e, int cx0, int cy0,
     // (the pixel's own cell, which the reference never votes) is taken back afterwards.
     const int xb = (x - cx0) * 1024, yb = (y - cy0) * 1024;
     int x1 = xb + t_lo * sx, y1 = yb + t_lo * sy;
-#pragma unroll 4
+#pragma unroll UNROLL
     for (int t = t_lo; t <= t_hi; t++, x1 += sx, y1 += sy) atomicAdd(s_acc + (y1 >> 10) * AP + (x1 >> 10), 1);
     if (t_lo <= 0 && t_hi >= 0) atomicAdd(s_acc + (y - cy0) * AP + (x - cx0), -1);
 }
 
+template <int UNROLL>
 __global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks2(const uint2 *__restrict__ edges,
                                                               const int2 *__restrict__ dir, int nbx, int nby, int h,
                                                               int w, int32_t *cand, int32_t *ncand, int cand_cap)
@@ -397,7 +399,7 @@ __global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks2(const uint2 *__res
             const uint2 e = __ldg(elist + s_boff[b] + (it - s_bend[b]));
             const int x = e.x & 0xffff, y = e.x >> 16;
             if (e.y == 0 || x < rx0 || x > rx1 || y < ry0 || y > ry1) continue;
-            vote_item(s_acc, e, cx0, cy0, X0, X1, Y0, Y1);
+            vote_item<UNROLL>(s_acc, e, cx0, cy0, X0, X1, Y0, Y1);
         }
     }
     __syncthreads();
@@ -794,7 +796,7 @@ int hough_circles_maps(const MapSet &ms, int h, int w, float *mcirc, int32_t *mc
     }
     {
         ScopedSection sec(SEC_VOTE, st);
-        auto kern = legacy_enabled("vote") ? k_vote_peaks : k_vote_peaks2;
+        auto kern = legacy_enabled("vote") ? k_vote_peaks : legacy_enabled("vote8") ? k_vote_peaks2<8> : k_vote_peaks2<4>;
         I2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, VOTE_SMEM));
         kern<<<dim3(cdiv(w, AT), cdiv(h, AT), maps), VOTE_THREADS, VOTE_SMEM, st>>>(edges, dir, nbx, nby, h, w, cand, ncand,
                                                                                    lim.cand_cap);

@@ -258,6 +258,30 @@ def test_batch_equals_oracle_1024(api, oracle):
             assert_same(rec[i]["board"].reshape(19, 19), truth[i], f"truth {i}")
 
 
+def test_multistream_runner_equals_single_stream(api, oracle):
+    """bench.py's default runner alternates chunks between several CUDA streams (one engine and
+    workspace per stream): the records must not depend on it.  Noisy, numbered stones (config 5
+    flavour) so that hysteresis has real weak-pixel work in every map."""
+    import torch
+    from img2sgf_b200 import batch as B, synth
+    imgs = [synth.to_rgb(synth.diagram(512, 24, 11, seed=40 + k, noise=2.5 if k % 2 else 0.0, numbered=(k % 3 == 0))[0])
+            for k in range(7)]
+    rgb = np.stack(imgs)
+    dev = torch.from_numpy(rgb).cuda()
+    one = B.records_to_numpy(B.BatchRunner(512, 512, chunk=2, streams=1).run(dev, 60))
+    many = B.records_to_numpy(B.BatchRunner(512, 512, chunk=2, streams=3).run(dev, 60))
+    torch.cuda.synchronize()
+    assert one.tobytes() == many.tobytes()
+    for i in (0, 1, 3):
+        res, circles, _ = oracle.pipeline(rgb[i], 60)
+        assert one[i]["status"] == 0 and one[i]["n_circles"] == res.n_circles
+        want = np.zeros((19, 19), np.uint8)
+        if res.board_ready:
+            b = oracle.board_of(res)
+            want[:b.shape[0], :b.shape[1]] = b
+        assert_same(one[i]["board"].reshape(19, 19), want, f"board {i}")
+
+
 def test_full_size_properties_2048(api):
     """BASELINE.json configs[2] shape (2048x2048, s=60, r=28, threshold 176): size-independent
     properties instead of an oracle run -- the generator's ground truth is recovered exactly
