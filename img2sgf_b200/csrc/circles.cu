@@ -796,7 +796,7 @@ int hough_circles_maps(const MapSet &ms, int h, int w, float *mcirc, int32_t *mc
     }
     {
         ScopedSection sec(SEC_VOTE, st);
-        auto kern = legacy_enabled("vote") ? k_vote_peaks : legacy_enabled("vote8") ? k_vote_peaks2<8> : k_vote_peaks2<4>;
+        auto kern = legacy_enabled("vote") ? k_vote_peaks : legacy_enabled("vote4") ? k_vote_peaks2<4> : k_vote_peaks2<8>;
         I2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, VOTE_SMEM));
         kern<<<dim3(cdiv(w, AT), cdiv(h, AT), maps), VOTE_THREADS, VOTE_SMEM, st>>>(edges, dir, nbx, nby, h, w, cand, ncand,
                                                                                    lim.cand_cap);
