@@ -856,9 +856,7 @@ int find_circles(const uint8_t *grey, const uint8_t *edges, int n, int h, int w,
     // internal order: grey, edges, med3, gau3, med5, gau5, med7, gau7
     int rc;
     if ((rc = i2s_gauss357(grey, blur[1], blur[3], blur[5], n, h, w, st))) return rc;
-    if ((rc = i2s_median(grey, blur[0], n, h, w, 3, st))) return rc;
-    if ((rc = i2s_median(grey, blur[2], n, h, w, 5, st))) return rc;
-    if ((rc = i2s_median(grey, blur[4], n, h, w, 7, st))) return rc;
+    if ((rc = median357(grey, blur[0], blur[2], blur[4], n, h, w, st))) return rc;
     MapSet ms{};
     ms.src[0] = grey; ms.src[1] = edges;
     for (int k = 0; k < 6; k++) ms.src[2 + k] = blur[k];

@@ -10,6 +10,7 @@ namespace i2s {
 void set_error(const char *fmt, ...);
 void count_launch();
 bool legacy_enabled(const char *name);
+int median357(const uint8_t *src, uint8_t *d3, uint8_t *d5, uint8_t *d7, int n, int h, int w, cudaStream_t st);
 
 #define I2S_CHECK_LAUNCH(what)                                              \
     do {                                                                    \

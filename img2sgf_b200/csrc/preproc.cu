@@ -248,30 +248,113 @@ __global__ void __launch_bounds__(GR_WARPS * 32) k_gauss357_roll(const uint8_t *
 // popcounts per pixel, no sorting network, no histogram.
 constexpr int MT_W = 64, MT_H = 32;
 
-template <int B> __global__ void __launch_bounds__(256) k_median(const uint8_t *__restrict__ src,
-                                                                 uint8_t *__restrict__ dst, int h, int w, bool al,
-                                                                 bool bulk)
+// Median of the B x B windows of 4 adjacent pixels (row ty, columns gx..gx+3 of the tile) from the bit
+// planes of a tile staged with a halo of RS rows / HX columns.  Warp-uniform control flow (one
+// __any_sync): call it with all 32 lanes.  Returns the 4 result bytes.
+template <int B, int RS, int HX, int SH, int GW>
+__device__ __forceinline__ uint32_t median4_planes(const uint32_t (&s_bits)[10][SH][GW + 1], int ty, int gx, bool live)
 {
-    constexpr int R = B / 2, HX = 16;                // x halo 16: bulk-copy rows are 16-byte aligned
-    constexpr int SW = MT_W + 2 * HX, SH = MT_H + 2 * R;
-    constexpr int GW = (SW + 31) / 32;               // 32-pixel groups per tile row
     constexpr int F = B + 3;                         // window columns of 4 adjacent pixels
     constexpr int RPW = 32 / F;                      // window rows packed per 32-bit word
     constexpr int NW = (B + RPW - 1) / RPW;          // words per window
     constexpr int KM = (B * B) / 2 + 1;              // a value held by KM window pixels is the median
+    constexpr int RO = RS - B / 2;                   // first window row inside the staged halo
+    // per-word masks of the B low bits of every packed row field
+    uint32_t fm[NW];
+#pragma unroll
+    for (int wd = 0; wd < NW; wd++) {
+        fm[wd] = 0;
+#pragma unroll
+        for (int r = wd * RPW; r < B && r < (wd + 1) * RPW; r++) fm[wd] |= ((1u << B) - 1u) << ((r - wd * RPW) * F);
+    }
+    const int start = gx + HX - B / 2, wi = start >> 5, sh = start & 31;
+    // window bits of one plane for the 4 adjacent pixels: rows packed at a stride of F bits
+    auto gather = [&](int pl, uint32_t (&P)[NW]) {
+#pragma unroll
+        for (int wd = 0; wd < NW; wd++) P[wd] = 0;
+#pragma unroll
+        for (int r = 0; r < B; r++) {
+            const uint32_t *rw = &s_bits[pl][ty + RO + r][wi];
+            uint32_t bits = __funnelshift_r(rw[0], rw[1], sh) & ((1u << F) - 1u);
+            P[r / RPW] |= bits << ((r % RPW) * F);
+        }
+    };
+    // Shortcut (exact): if at least KM of the B*B window pixels equal 255 the median is 255, likewise
+    // for 0.  Printed diagrams are mostly saturated paper and ink, so most warps finish here.
+    uint32_t packed = 0;
+    bool open = false;                               // some pixel of this thread still needs the selection
+    {
+        uint32_t P255[NW], P0[NW];
+        gather(8, P255);
+        gather(9, P0);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int c255 = 0, c0 = 0;
+#pragma unroll
+            for (int wd = 0; wd < NW; wd++) {
+                c255 += __popc((P255[wd] >> j) & fm[wd]);
+                c0 += __popc((P0[wd] >> j) & fm[wd]);
+            }
+            if (c255 >= KM) packed |= 0xffu << (8 * j);
+            else if (c0 < KM) open = true;
+        }
+    }
+    if (__any_sync(0xffffffffu, open && live)) {
+        uint32_t P[8][NW];
+#pragma unroll
+        for (int bit = 0; bit < 8; bit++) gather(bit, P[bit]);
+        packed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t C[NW];
+#pragma unroll
+            for (int wd = 0; wd < NW; wd++) C[wd] = fm[wd];
+            int k = (B * B) / 2;
+            uint32_t val = 0;
+#pragma unroll
+            for (int bit = 7; bit >= 0; bit--) {
+                uint32_t Z[NW], O[NW];
+                int nz = 0;
+#pragma unroll
+                for (int wd = 0; wd < NW; wd++) {
+                    uint32_t pj = P[bit][wd] >> j;
+                    Z[wd] = C[wd] & ~pj;
+                    O[wd] = C[wd] & pj;
+                    nz += __popc(Z[wd]);
+                }
+                const bool zero = k < nz;              // the median has a 0 in this bit
+#pragma unroll
+                for (int wd = 0; wd < NW; wd++) C[wd] = zero ? Z[wd] : O[wd];
+                if (!zero) { k -= nz; val |= 1u << bit; }
+            }
+            packed |= val << (8 * j);
+        }
+    }
+    return packed;
+}
+
+// MASK selects the window sizes computed from ONE staged tile and ONE set of bit planes:
+// bit 0 -> 3x3 into dst3, bit 1 -> 5x5 into dst5, bit 2 -> 7x7 into dst7.
+template <int MASK> __global__ void __launch_bounds__(256, 4) k_median(const uint8_t *__restrict__ src,
+                                                                    uint8_t *__restrict__ dst3, uint8_t *__restrict__ dst5,
+                                                                    uint8_t *__restrict__ dst7, int h, int w, bool al,
+                                                                    bool bulk)
+{
+    constexpr int RS = (MASK & 4) ? 3 : (MASK & 2) ? 2 : 1, HX = 16;   // x halo 16: bulk-copy rows are 16-byte aligned
+    constexpr int SW = MT_W + 2 * HX, SH = MT_H + 2 * RS;
+    constexpr int GW = (SW + 31) / 32;               // 32-pixel groups per tile row
     __shared__ __align__(128) uint8_t s_in[SH * SW];
     __shared__ uint32_t s_bits[10][SH][GW + 1];      // planes 0..7: bits of the pixel; 8: pixel == 255; 9: pixel == 0
     __shared__ uint64_t s_bar;
     const size_t plane = (size_t)h * w;
     const uint8_t *img = src + blockIdx.z * plane;
-    uint8_t *out = dst + blockIdx.z * plane;
     const int x0 = blockIdx.x * MT_W, y0 = blockIdx.y * MT_H;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    stage_tile_bulk(s_in, img, h, w, x0 - HX, y0 - R, SW, SH, BORDER_REPLICATE, bulk, al, &s_bar);
+    stage_tile_bulk(s_in, img, h, w, x0 - HX, y0 - RS, SW, SH, BORDER_REPLICATE, bulk, al, &s_bar);
     {   // bit planes: s_bits[b][row][g] bit i = bit b of tile pixel (row, 32 g + i).  A thread turns
         // 8 adjacent pixels into one byte of every plane: bit b of the 4 bytes of a word is gathered
         // into a nibble by one multiply ((x & 0x01010101) * 0x01020408 puts byte j's bit at 24 + j).
-        static_assert(SW % 8 == 0, "whole bytes of a plane row");
+        static_assert(SW % 32 == 0, "whole words of a plane row");
         uint8_t *planes = reinterpret_cast<uint8_t *>(&s_bits[0][0][0]);
         constexpr int ROWB = (GW + 1) * 4, PLB = SH * ROWB;           // bytes per plane row / per plane
         auto nib = [](uint32_t v) { return ((v & 0x01010101u) * 0x01020408u) >> 24; };
@@ -286,96 +369,24 @@ template <int B> __global__ void __launch_bounds__(256) k_median(const uint8_t *
             dstb[9 * PLB] = (uint8_t)(nib(all8(~v.x)) | (nib(all8(~v.y)) << 4));
         }
         for (int i = threadIdx.x; i < 10 * SH; i += blockDim.x) s_bits[i / SH][i % SH][GW] = 0;   // pad word
-        if (SW % 32 != 0)                                             // bytes of the last word beyond the tile
-            for (int i = threadIdx.x; i < 10 * SH * (4 - (SW / 8) % 4); i += blockDim.x) {
-                const int pr = i / (4 - (SW / 8) % 4), kk = SW / 8 + i % (4 - (SW / 8) % 4);
-                planes[pr * ROWB + kk] = 0;
-            }
     }
     __syncthreads();
-    // per-word masks of the B low bits of every packed row field
-    uint32_t fm[NW];
-#pragma unroll
-    for (int wd = 0; wd < NW; wd++) {
-        fm[wd] = 0;
-#pragma unroll
-        for (int r = wd * RPW; r < B && r < (wd + 1) * RPW; r++) fm[wd] |= ((1u << B) - 1u) << ((r - wd * RPW) * F);
-    }
     // A warp covers a compact 16 x 8 pixel patch (lane = 4-pixel group lane%4 of row lane/4), so that
-    // the saturated-window shortcut below applies to whole warps as often as possible.
+    // the saturated-window shortcut applies to whole warps as often as possible.
     for (int q = warp; q < (MT_W / 16) * (MT_H / 8); q += 8) {
         const int ty = (q / (MT_W / 16)) * 8 + (lane >> 2), gx = ((q % (MT_W / 16)) * 4 + (lane & 3)) * 4;
         const int y = y0 + ty, x = x0 + gx;
         const bool live = y < h && x < w;
-        const int start = gx + HX - R, wi = start >> 5, sh = start & 31;
-        // window bits of one plane for the 4 adjacent pixels: rows packed at a stride of F bits
-        auto gather = [&](int pl, uint32_t (&P)[NW]) {
-#pragma unroll
-            for (int wd = 0; wd < NW; wd++) P[wd] = 0;
-#pragma unroll
-            for (int r = 0; r < B; r++) {
-                const uint32_t *rw = &s_bits[pl][ty + r][wi];
-                uint32_t bits = __funnelshift_r(rw[0], rw[1], sh) & ((1u << F) - 1u);
-                P[r / RPW] |= bits << ((r % RPW) * F);
-            }
-        };
-        // Shortcut (exact): if at least KM of the B*B window pixels equal 255 the median is 255, likewise
-        // for 0.  Printed diagrams are mostly saturated paper and ink, so most warps finish here.
-        uint32_t packed = 0;
-        bool open = false;                           // some pixel of this thread still needs the selection
-        {
-            uint32_t P255[NW], P0[NW];
-            gather(8, P255);
-            gather(9, P0);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                int c255 = 0, c0 = 0;
-#pragma unroll
-                for (int wd = 0; wd < NW; wd++) {
-                    c255 += __popc((P255[wd] >> j) & fm[wd]);
-                    c0 += __popc((P0[wd] >> j) & fm[wd]);
-                }
-                if (c255 >= KM) packed |= 0xffu << (8 * j);
-                else if (c0 < KM) open = true;
-            }
-        }
-        if (__any_sync(0xffffffffu, open && live)) {
-            uint32_t P[8][NW];
-#pragma unroll
-            for (int bit = 0; bit < 8; bit++) gather(bit, P[bit]);
-            packed = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                uint32_t C[NW];
-#pragma unroll
-                for (int wd = 0; wd < NW; wd++) C[wd] = fm[wd];
-                int k = (B * B) / 2;
-                uint32_t val = 0;
-#pragma unroll
-                for (int bit = 7; bit >= 0; bit--) {
-                    uint32_t Z[NW], O[NW];
-                    int nz = 0;
-#pragma unroll
-                    for (int wd = 0; wd < NW; wd++) {
-                        uint32_t pj = P[bit][wd] >> j;
-                        Z[wd] = C[wd] & ~pj;
-                        O[wd] = C[wd] & pj;
-                        nz += __popc(Z[wd]);
-                    }
-                    const bool zero = k < nz;              // the median has a 0 in this bit
-#pragma unroll
-                    for (int wd = 0; wd < NW; wd++) C[wd] = zero ? Z[wd] : O[wd];
-                    if (!zero) { k -= nz; val |= 1u << bit; }
-                }
-                packed |= val << (8 * j);
-            }
-        }
-        if (live) {
-            size_t o = (size_t)y * w + x;
-            if (al && x + 3 < w) *reinterpret_cast<uint32_t *>(out + o) = packed;
+        const size_t o = blockIdx.z * plane + (size_t)y * w + x;
+        auto store4 = [&](uint8_t *dst, uint32_t packed) {
+            if (!live) return;
+            if (al && x + 3 < w) *reinterpret_cast<uint32_t *>(dst + o) = packed;
             else
-                for (int k2 = 0; k2 < 4 && x + k2 < w; k2++) out[o + k2] = (uint8_t)(packed >> (8 * k2));
-        }
+                for (int k2 = 0; k2 < 4 && x + k2 < w; k2++) dst[o + k2] = (uint8_t)(packed >> (8 * k2));
+        };
+        if (MASK & 4) store4(dst7, median4_planes<7, RS, HX, SH, GW>(s_bits, ty, gx, live));
+        if (MASK & 2) store4(dst5, median4_planes<5, RS, HX, SH, GW>(s_bits, ty, gx, live));
+        if (MASK & 1) store4(dst3, median4_planes<3, RS, HX, SH, GW>(s_bits, ty, gx, live));
     }
 }
 
@@ -549,6 +560,26 @@ extern "C" int i2s_gauss357(const uint8_t *src, uint8_t *dst3, uint8_t *dst5, ui
     return I2S_OK;
 }
 
+// medianBlur 3, 5 and 7 of the same images from one staged tile and one set of bit planes (the blur
+// pyramid of img2sgf.py:171-175 needs all three).  Internal to the library (find_circles).
+int i2s::median357(const uint8_t *src, uint8_t *d3, uint8_t *d5, uint8_t *d7, int n, int h, int w, cudaStream_t st)
+{
+    if (n == 0) return I2S_OK;
+    if (legacy_enabled("med357")) {
+        int rc;
+        if ((rc = i2s_median(src, d3, n, h, w, 3, st))) return rc;
+        if ((rc = i2s_median(src, d5, n, h, w, 5, st))) return rc;
+        return i2s_median(src, d7, n, h, w, 7, st);
+    }
+    dim3 grid(cdiv(w, MT_W), cdiv(h, MT_H), n);
+    ScopedSection sec(SEC_MEDIAN, st);
+    bool al = (w & 3) == 0 && (((uintptr_t)src | (uintptr_t)d3 | (uintptr_t)d5 | (uintptr_t)d7) & 3) == 0;
+    bool bulk = (w & 15) == 0 && ((uintptr_t)src & 15) == 0;
+    k_median<7><<<grid, 256, 0, st>>>(src, d3, d5, d7, h, w, al, bulk);
+    I2S_CHECK_LAUNCH("k_median");
+    return I2S_OK;
+}
+
 extern "C" int i2s_median(const uint8_t *src, uint8_t *dst, int n, int h, int w, int b, void *stream)
 {
     I2S_ARG(src && dst && n >= 0 && h > 0 && w > 0 && (b == 1 || b == 3 || b == 5 || b == 7));
@@ -565,9 +596,9 @@ extern "C" int i2s_median(const uint8_t *src, uint8_t *dst, int n, int h, int w,
     } else if (b == 5) {
         // bit planes + saturated-window shortcut beat the 99-exchange network on diagram content
         if (legacy_enabled("med5net")) k_median_net<5><<<grid, 256, 0, st>>>(src, dst, h, w, al, bulk);
-        else k_median<5><<<grid, 256, 0, st>>>(src, dst, h, w, al, bulk);
+        else k_median<2><<<grid, 256, 0, st>>>(src, nullptr, dst, nullptr, h, w, al, bulk);
     } else {
-        k_median<7><<<grid, 256, 0, st>>>(src, dst, h, w, al, bulk);
+        k_median<4><<<grid, 256, 0, st>>>(src, nullptr, nullptr, dst, h, w, al, bulk);
     }
     I2S_CHECK_LAUNCH("k_median");
     return I2S_OK;
