@@ -9,7 +9,7 @@ Workload (BASELINE.json configs[3]): synthetic 1024x1024 diagrams (s=50, r=24, l
 pinned to 150), 1024 images per GPU (8192 over 8 GPUs), the whole path
 RGB array -> 19x19 board record, weak scaling over image shards with one NCCL all-gather of
 the 384-byte records.  A "step" is one pass of the path over the rank's whole batch, in chunks
-of 32 images alternating between 4 CUDA streams.
+of 32 images alternating between 8 CUDA streams.
 
 `value`  : images/s with the inputs already resident in HBM (CUDA events, max over ranks).
 `e2e`    : the same through the public API with HOST (pinned) buffers: H2D of every image and
@@ -440,7 +440,7 @@ def main():
     ap.add_argument("--workload", default="synth1024", choices=sorted(WORKLOADS))
     ap.add_argument("--per-gpu", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
-    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--streams", type=int, default=8)
     ap.add_argument("--cpu-images", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
