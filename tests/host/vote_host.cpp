@@ -1,0 +1,100 @@
+// vote_host.cpp -- CPU restatement of the tile scheme of k_vote_peaks2 (img2sgf_b200/csrc/circles.cu):
+// 128x128 accumulator tiles with a 1-cell ring and a 2-cell guard band, every edge pixel within reach
+// clipped to the tile by a conservative float interval of the signed radius, ONE loop over that
+// interval with the vote at t = 0 taken back, column w / row h cleared, 4-neighbour peak scan.
+// Test infrastructure: shows on the CPU that the scheme reproduces the reference accumulator's peaks
+// exactly (the GPU parity tests show it for the kernel itself).  The kernel's approximate divide is
+// replaced by an exact one here; SLACK widens the interval like the kernel does.
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+
+namespace {
+constexpr int MAX_R = 30, ACC_THR = 30;
+constexpr int AT = 128, AG = 2, AS = AT + 2 + 2 * AG, AP = AS + 1;
+
+int cv_round(float v) { return (int)nearbyintf(v); }
+}  // namespace
+
+// img: h x w grey, edges: h x w (0/255, the Canny output the votes are cast from).
+// out_peaks: linear indices cy * (w + 2) + cx of the accumulator peaks, unsorted; returns their number,
+// or -1 if a vote ever left the shared tile (guard band too small) -- must never happen.
+extern "C" int vh_vote_peaks(const uint8_t *img, const uint8_t *edges, int h, int w, float slack, int *out_peaks, int cap,
+                             long long *votes_cast)
+{
+    struct Item { int x, y, sx, sy; };
+    std::vector<Item> items;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            if (!edges[(size_t)y * w + x]) continue;
+            const int xm = x > 0 ? x - 1 : 0, xp = x < w - 1 ? x + 1 : w - 1;
+            const int ym = y > 0 ? y - 1 : 0, yp = y < h - 1 ? y + 1 : h - 1;
+#define P(yy, xx) ((int)img[(size_t)(yy) * w + (xx)])
+            const int dx = (P(ym, xp) + 2 * P(y, xp) + P(yp, xp)) - (P(ym, xm) + 2 * P(y, xm) + P(yp, xm));
+            const int dy = (P(yp, xm) + 2 * P(yp, x) + P(yp, xp)) - (P(ym, xm) + 2 * P(ym, x) + P(ym, xp));
+#undef P
+            if (dx == 0 && dy == 0) continue;
+            const float vx = (float)dx, vy = (float)dy;
+            const float mag = sqrtf(vx * vx + vy * vy);
+            if (mag < 1.0f) continue;
+            items.push_back({x, y, cv_round(vx * 1024.0f / mag), cv_round(vy * 1024.0f / mag)});
+        }
+    int n = 0;
+    long long cast = 0;
+    std::vector<int> acc(AS * AP);
+    for (int ty0 = 0; ty0 < h; ty0 += AT)
+        for (int tx0 = 0; tx0 < w; tx0 += AT) {
+            std::fill(acc.begin(), acc.end(), 0);
+            const int cx0 = tx0 - 1 - AG, cy0 = ty0 - 1 - AG;
+            const int X0 = std::max(tx0 - 1, 0), X1 = std::min(tx0 + AT, w - 1);
+            const int Y0 = std::max(ty0 - 1, 0), Y1 = std::min(ty0 + AT, h - 1);
+            const int rx0 = std::max(tx0 - 1 - MAX_R, 0), rx1 = std::min(tx0 + AT + MAX_R, w - 1);
+            const int ry0 = std::max(ty0 - 1 - MAX_R, 0), ry1 = std::min(ty0 + AT + MAX_R, h - 1);
+            for (const Item &e : items) {
+                const int x = e.x, y = e.y, sx = e.sx, sy = e.sy;
+                if (x < rx0 || x > rx1 || y < ry0 || y > ry1) continue;
+                float lo = -(float)MAX_R, hi = (float)MAX_R;
+                if (sx != 0) {
+                    const float inv = 1024.0f / (float)sx;
+                    const float ta = (float)(X0 - x) * inv, tb = (float)(X1 + 1 - x) * inv;
+                    lo = fmaxf(lo, fminf(ta, tb)); hi = fminf(hi, fmaxf(ta, tb));
+                } else if (x < X0 || x > X1) continue;
+                if (sy != 0) {
+                    const float inv = 1024.0f / (float)sy;
+                    const float ta = (float)(Y0 - y) * inv, tb = (float)(Y1 + 1 - y) * inv;
+                    lo = fmaxf(lo, fminf(ta, tb)); hi = fminf(hi, fmaxf(ta, tb));
+                } else if (y < Y0 || y > Y1) continue;
+                const int t_lo = std::max(-MAX_R, (int)floorf(lo - slack)), t_hi = std::min(MAX_R, (int)ceilf(hi + slack));
+                if (t_lo > t_hi) continue;
+                const int xb = (x - cx0) * 1024, yb = (y - cy0) * 1024;
+                int x1 = xb + t_lo * sx, y1 = yb + t_lo * sy;
+                for (int t = t_lo; t <= t_hi; t++, x1 += sx, y1 += sy) {
+                    const int ly = y1 >> 10, lx = x1 >> 10;
+                    if (ly < 0 || ly >= AS || lx < 0 || lx >= AS) return -1;
+                    acc[ly * AP + lx]++;
+                    cast++;
+                }
+                if (t_lo <= 0 && t_hi >= 0) acc[(y - cy0) * AP + (x - cx0)]--;
+            }
+            if (w - cx0 < AS)
+                for (int ly = 0; ly < AS; ly++) acc[ly * AP + (w - cx0)] = 0;
+            if (h - cy0 < AS)
+                for (int lx = 0; lx < AS; lx++) acc[(h - cy0) * AP + lx] = 0;
+            for (int ty = 0; ty < AT; ty++)
+                for (int tx = 0; tx < AT; tx++) {
+                    const int cx = tx0 + tx, cy = ty0 + ty;
+                    if (cx < 1 || cy < 1 || cx >= w || cy >= h) continue;
+                    const int *c = acc.data() + (ty + 1 + AG) * AP + tx + 1 + AG;
+                    const int v = c[0];
+                    if (v > ACC_THR && v > c[-1] && v >= c[1] && v > c[-AP] && v >= c[AP]) {
+                        if (n < cap) out_peaks[n] = cy * (w + 2) + cx;
+                        n++;
+                    }
+                }
+        }
+    if (votes_cast) *votes_cast = cast;
+    return n;
+}
