@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(256) k_state_to_edges4(const uint32_t *__restr
     }
 }
 
-constexpr int HYST_MAX_PASSES = 64;
+constexpr int HYST_MAX_PASSES = 64;               // size of the per-pass list-counter ring, not a limit on passes
 
 size_t canny_scratch_bytes(int maps, int h, int w)
 {
@@ -571,7 +571,6 @@ int hysteresis(uint8_t *state, int maps, int n_images, int h, int w, int passes,
     int *list = (int *)(d1 + align_up(tiles, 256));
     int *counts = (int *)((uint8_t *)list + align_up(tiles * sizeof(int), 256));
     const bool sparse = !legacy_enabled("hystdense");
-    if (passes > HYST_MAX_PASSES) passes = HYST_MAX_PASSES;
     if (sparse) I2S_CUDA(cudaMemsetAsync(counts, 0, HYST_MAX_PASSES * sizeof(int), st));
     static bool attr2_done = false;
     if (!attr2_done) {
@@ -582,10 +581,12 @@ int hysteresis(uint8_t *state, int maps, int n_images, int h, int w, int passes,
         uint8_t *din = (p & 1) ? d1 : d0, *dout = (p & 1) ? d0 : d1;
         const bool check = p > 0 || tiles_flagged;
         if (check && sparse) {
-            k_hyst_list<<<(unsigned)min((size_t)592, (tiles + 255) / 256), 256, 0, st>>>(din, (int)tiles, list, counts + p);
+            int *cnt = counts + p % HYST_MAX_PASSES;           // the counters are a ring: re-zero a slot before reuse
+            if (p >= HYST_MAX_PASSES) I2S_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int), st));
+            k_hyst_list<<<(unsigned)min((size_t)592, (tiles + 255) / 256), 256, 0, st>>>(din, (int)tiles, list, cnt);
             I2S_CHECK_LAUNCH("k_hyst_list");
-            k_hysteresis_list<<<(unsigned)min((size_t)(148 * 4), tiles), 256, kSmem, st>>>(state, h, w, tx, ty, list, counts + p,
-                                                                                            din, dout, al, bulk);
+            k_hysteresis_list<<<(unsigned)min((size_t)(148 * 4), tiles), 256, kSmem, st>>>(state, h, w, tx, ty, list, cnt, din,
+                                                                                            dout, al, bulk);
         } else {
             k_hysteresis<<<(unsigned)tiles, 256, kSmem, st>>>(state, h, w, tx, ty, din, dout, check ? 1 : 0, al, bulk);
         }
