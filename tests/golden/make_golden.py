@@ -88,6 +88,11 @@ def main():
             rv[p + "contrast"] = np.array(R.enhance(Image.fromarray(img)))
     np.savez_compressed(os.path.join(HERE, "random_vectors.npz"), **rv)
     print("wrote golden.npz, random_vectors.npz")
+    # the goldens came from the replay (oracle/ref_replay.py): prove they equal what the reference's
+    # own source produces (img2sgf.py Parts 1-3 executed unmodified)
+    import check_against_reference
+    if check_against_reference.main(["--log", os.path.join(HERE, "..", "..", "profiles", "r2_reference_pin.txt")]) != 0:
+        raise SystemExit("goldens differ from the reference's own code")
 
 
 if __name__ == "__main__":

@@ -56,3 +56,14 @@ def test_random_sparse_lines(seed, oracle):
         np.testing.assert_array_equal(np.asarray(ref, np.float32).reshape(-1), got.reshape(-1))
         ref_c = R.cluster(ref) if len(ref) else []
         np.testing.assert_array_equal(np.asarray(ref_c, np.float64), oracle.cluster(got))
+
+
+@pytest.mark.skipif(not __import__("os").path.exists("/root/reference/img2sgf.py"),
+                    reason="the reference source exists in the build container only")
+def test_goldens_pinned_to_reference_source():
+    """The committed goldens equal what the reference's OWN code (img2sgf.py Parts 1-3, executed
+    unmodified with GUI stand-ins) leaves in its globals for the 18 test images."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import check_against_reference as chk
+    assert chk.main([]) == 0
