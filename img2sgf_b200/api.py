@@ -4,13 +4,15 @@ the sm_100a kernels through the C ABI in include/img2sgf_b200.h.
 The reference passes everything through module globals and Tk getters; here
 every input is an explicit argument, names and return conventions are the reference's:
 
+    enhance(rgb, fc, fb)                            img2sgf.py:142-149
     edge_map(rgb)                                   img2sgf.py:162-165
     find_circles(grey, edges) -> circles, masked    img2sgf.py:169-198
     find_lines(masked, threshold, direction)        img2sgf.py:230-255   ([] when nothing found)
     cluster(lines)                                  img2sgf.py:268-292   ([] when < 2 lines)
     validate_grid(hcentres, vcentres, circles)      img2sgf.py:420-445
     classify_stones(grey, circles, ...)             img2sgf.py:497-515,537-542
-    process_image(rgb, ...)                         img2sgf.py:153-204 + find_grid :546-576
+    process_image(rgb, ...)                         img2sgf.py:142-204 + find_grid :546-576
+    process_images([rgb, ...])                      the same for a batch of images of any sizes
 
 PyTorch is used only as the device-buffer carrier (allocation, H2D/D2H copies, stream handle).
 There is no CPU fallback: without a CUDA device or the built library these functions raise.
@@ -107,19 +109,36 @@ def grey_image(rgb: np.ndarray) -> np.ndarray:
     h, w = rgb.shape[:2]
     d = _dev(rgb, np.uint8)
     out = _empty((h, w), torch.uint8)
-    N.check(N.lib().i2s_grey(_ptr(d), _ptr(out), 1, h, w, _stream()), "i2s_grey")
+    N.check(N.lib().i2s_grey(_ptr(d), 0, _ptr(out), 0, 1, h, w, _stream()), "i2s_grey")
     return out.cpu().numpy()
 
 
-def contrast(rgb: np.ndarray, factor: float) -> np.ndarray:
-    """ImageEnhance.Contrast(img).enhance(factor) -- img2sgf.py:142-144."""
+def enhance(rgb: np.ndarray, contrast_factor: float = 1.0, brightness_factor: float = 1.0) -> np.ndarray:
+    """ImageEnhance.Contrast(img).enhance(fc) then ImageEnhance.Brightness(img).enhance(fb) --
+    img2sgf.py:142-149 (fc = 102/(101-contrast)-1, fb = 450/(200-brightness)-2)."""
     _require_cuda()
     h, w = rgb.shape[:2]
     d = _dev(rgb, np.uint8)
     out = torch.empty_like(d)
     scratch = _empty((8,), torch.uint8)
-    N.check(N.lib().i2s_contrast(_ptr(d), _ptr(out), _ptr(scratch), 1, h, w, float(factor), _stream()), "i2s_contrast")
+    N.check(N.lib().i2s_enhance(_ptr(d), 0, _ptr(out), 0, _ptr(scratch), 1, h, w, float(contrast_factor),
+                                float(brightness_factor), _stream()), "i2s_enhance")
     return out.cpu().numpy()
+
+
+def contrast(rgb: np.ndarray, factor: float) -> np.ndarray:
+    """ImageEnhance.Contrast(img).enhance(factor) -- img2sgf.py:142-144."""
+    return enhance(rgb, factor, 1.0)
+
+
+def scaled_contrast(slider: float) -> float:
+    """img2sgf.py:142: slider range 0-100 -> factor 0.01-101, 50 -> 1.0."""
+    return 102 / (101 - slider) - 1
+
+
+def scaled_brightness(slider: float) -> float:
+    """img2sgf.py:147: slider range 0-100 -> factor 0.25-2.5, 50 -> 1.0."""
+    return 450 / (200 - slider) - 2
 
 
 def gaussian_blurs(grey: np.ndarray):
@@ -128,7 +147,7 @@ def gaussian_blurs(grey: np.ndarray):
     h, w = grey.shape
     d = _dev(grey, np.uint8)
     outs = [_empty((h, w), torch.uint8) for _ in range(3)]
-    N.check(N.lib().i2s_gauss357(_ptr(d), _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), 1, h, w, _stream()),
+    N.check(N.lib().i2s_gauss357(_ptr(d), _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), 1, h, w, 0, _stream()),
             "i2s_gauss357")
     return [o.cpu().numpy() for o in outs]
 
@@ -139,21 +158,23 @@ def median_blur(grey: np.ndarray, b: int) -> np.ndarray:
     h, w = grey.shape
     d = _dev(grey, np.uint8)
     out = _empty((h, w), torch.uint8)
-    N.check(N.lib().i2s_median(_ptr(d), _ptr(out), 1, h, w, int(b), _stream()), "i2s_median")
+    N.check(N.lib().i2s_median(_ptr(d), _ptr(out), 1, h, w, 0, int(b), _stream()), "i2s_median")
     return out.cpu().numpy()
 
 
-def _canny(img: np.ndarray, channels: int, low: int, high: int) -> np.ndarray:
+def _canny(img: np.ndarray, channels: int, low: int, high: int, hyst_passes=None) -> np.ndarray:
     _require_cuda()
     h, w = img.shape[:2]
     d = _dev(img, np.uint8)
 
     def run(lim):
+        if hyst_passes is not None:
+            lim = N.Limits(lim.cand_cap, lim.circle_cap, lim.line_cap, max(int(hyst_passes), lim.hyst_passes))
         out = _empty((h, w), torch.uint8)
         status = torch.zeros(1, dtype=torch.int32, device="cuda")
         nb = N.lib().i2s_canny_workspace_bytes(1, h, w)
         ws = _empty((nb,), torch.uint8)
-        N.check(N.lib().i2s_canny(_ptr(d), channels, _ptr(out), 1, h, w, int(low), int(high), lim.hyst_passes,
+        N.check(N.lib().i2s_canny(_ptr(d), channels, 0, _ptr(out), 0, 1, h, w, int(low), int(high), lim.hyst_passes,
                                   _ptr(status), _ptr(ws), nb, _stream()), "i2s_canny")
         return out.cpu().numpy(), int(status.item())
 
@@ -165,12 +186,13 @@ def edge_map(rgb: np.ndarray, low: int = edge_min_default, high: int = edge_max_
     return _canny(rgb, 3, low, high)
 
 
-def canny_grey(img: np.ndarray, low: int = 50, high: int = 100) -> np.ndarray:
-    """The single-channel Canny cv.HoughCircles runs on its input (param1=100) -- img2sgf.py:180."""
-    return _canny(img, 1, low, high)
+def canny_grey(img: np.ndarray, low: int = 50, high: int = 100, hyst_passes=None) -> np.ndarray:
+    """The single-channel Canny cv.HoughCircles runs on its input (param1=100) -- img2sgf.py:180.
+    `hyst_passes` starts the cross-tile pass budget higher than the default (it is enlarged on demand anyway)."""
+    return _canny(img, 1, low, high, hyst_passes)
 
 
-def hough_circles(img: np.ndarray) -> np.ndarray:
+def hough_circles(img: np.ndarray, limits: N.Limits | None = None) -> np.ndarray:
     """cv.HoughCircles(img, HOUGH_GRADIENT, 1, 10, [], 100, 30, 1, 30)[0] -- img2sgf.py:180; (n,3) float32."""
     _require_cuda()
     h, w = img.shape
@@ -182,12 +204,12 @@ def hough_circles(img: np.ndarray) -> np.ndarray:
         status = torch.zeros(1, dtype=torch.int32, device="cuda")
         nb = N.lib().i2s_hough_circles_workspace_bytes(1, h, w, C.byref(lim))
         ws = _empty((nb,), torch.uint8)
-        N.check(N.lib().i2s_hough_circles(_ptr(d), 1, h, w, _ptr(circ), _ptr(cnt), _ptr(status), C.byref(lim),
+        N.check(N.lib().i2s_hough_circles(_ptr(d), 0, 1, h, w, _ptr(circ), _ptr(cnt), _ptr(status), C.byref(lim),
                                           _ptr(ws), nb, _stream()), "i2s_hough_circles")
         n = int(cnt.item())
         return circ[:min(n, lim.circle_cap)].cpu().numpy(), int(status.item())
 
-    return _retrying(run)
+    return _retrying(run, limits)
 
 
 def mask_circles(edges: np.ndarray, circles: np.ndarray) -> np.ndarray:
@@ -200,7 +222,7 @@ def mask_circles(edges: np.ndarray, circles: np.ndarray) -> np.ndarray:
     cap = max(len(c), 1)
     dc = _dev(c if len(c) else np.zeros((1, 3), np.float32))
     cnt = torch.tensor([len(c)], dtype=torch.int32, device="cuda")
-    N.check(N.lib().i2s_mask_circles(_ptr(d), _ptr(out), 1, h, w, _ptr(dc), _ptr(cnt), cap, _stream()),
+    N.check(N.lib().i2s_mask_circles(_ptr(d), _ptr(out), 0, 1, h, w, _ptr(dc), _ptr(cnt), cap, _stream()),
             "i2s_mask_circles")
     return out.cpu().numpy()
 
@@ -222,7 +244,7 @@ def find_circles(grey: np.ndarray, edges: np.ndarray):
         masked = _empty((h, w), torch.uint8)
         nb = N.lib().i2s_find_circles_workspace_bytes(1, h, w, C.byref(lim))
         ws = _empty((nb,), torch.uint8)
-        N.check(N.lib().i2s_find_circles(_ptr(dg), _ptr(de), 1, h, w, _ptr(circ), _ptr(cnt), _ptr(masked),
+        N.check(N.lib().i2s_find_circles(_ptr(dg), _ptr(de), 0, 1, h, w, _ptr(circ), _ptr(cnt), _ptr(masked),
                                          _ptr(status), C.byref(lim), _ptr(ws), nb, _stream()), "i2s_find_circles")
         n = int(cnt.item())
         return (circ[:min(n, lim.circle_cap)].cpu().numpy(), masked.cpu().numpy()), int(status.item())
@@ -241,7 +263,7 @@ def _find_lines_both(masked: np.ndarray, threshold: int):
         status = torch.zeros(1, dtype=torch.int32, device="cuda")
         nb = N.lib().i2s_find_lines_workspace_bytes(1, h, w)
         ws = _empty((nb,), torch.uint8)
-        N.check(N.lib().i2s_find_lines(_ptr(d), 1, h, w, int(threshold), _ptr(rho), _ptr(cnt), lim.line_cap,
+        N.check(N.lib().i2s_find_lines(_ptr(d), 0, 1, h, w, int(threshold), _ptr(rho), _ptr(cnt), lim.line_cap,
                                        _ptr(status), _ptr(ws), nb, _stream()), "i2s_find_lines")
         c = cnt.cpu().numpy()
         r = rho.cpu().numpy()
@@ -346,7 +368,7 @@ def classify_stones(grey: np.ndarray, circles, hcentres_complete, vcentres_compl
     dgrey = _dev(grey, np.uint8)
     rec = torch.zeros(N.RECORD_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
     br = torch.zeros(BOARD_SIZE * BOARD_SIZE, dtype=torch.float64, device="cuda")
-    N.check(N.lib().i2s_classify_stones(_ptr(dgrey), 1, h, w, _ptr(dc), _ptr(cnt), cap, _ptr(dgrid),
+    N.check(N.lib().i2s_classify_stones(_ptr(dgrey), 0, 1, h, w, _ptr(dc), _ptr(cnt), cap, _ptr(dgrid),
                                         int(black_stone_threshold), _ptr(rec), _ptr(br), _stream()),
             "i2s_classify_stones")
     r = rec.cpu().numpy().view(N.RECORD_DTYPE)[0]
@@ -359,10 +381,13 @@ def classify_stones(grey: np.ndarray, circles, hcentres_complete, vcentres_compl
 @dataclass
 class Processed:
     """Everything process_image()/find_grid() leave in the reference's globals (img2sgf.py:118-120,
-    498-499, 547-548), for one image."""
+    498-499, 547-548), for one image.  `circles` is the stacked list the ten HoughCircles calls give
+    (:179-186, what the masking loop uses); `circles_in_grid` is what the global `circles` holds after
+    find_grid(): the radius-filtered list when the grid is valid (:441-443, :555), else the same list."""
     grey_image_np: np.ndarray
     edge_detected_image_np: np.ndarray
     circles: np.ndarray
+    circles_in_grid: np.ndarray
     circles_removed_image_np: np.ndarray
     hlines: object
     vlines: object
@@ -376,28 +401,39 @@ class Processed:
     board_ready: bool
     detected_board: object
     full_board: object
+    stone_brightnesses: object
     num_black_stones: int
     num_white_stones: int
     record: object
 
 
 def process_image(rgb: np.ndarray, threshold: int | None = None,
-                  black_stone_threshold: int = black_stone_threshold_default) -> Processed:
-    """process_image() from the contrast-enhanced RGB array on (img2sgf.py:150) through find_grid()
-    and identify_board() -- one i2s_pipeline call."""
-    from .batch import Engine
+                  black_stone_threshold: int = black_stone_threshold_default, contrast_slider: float | None = None,
+                  brightness_slider: float | None = None) -> Processed:
+    """process_image() (img2sgf.py:117-204) through find_grid() and identify_board() -- one i2s_pipeline
+    call.  `rgb`: [h,w,3] u8 in PIL's RGB order, or [h,w] for a greyscale source.  By default the array
+    is taken as already contrast-enhanced (:150); with `contrast_slider` / `brightness_slider` (the GUI's
+    0..100 values, defaults 70 / 50) the prologue :142-149 runs on the device first."""
+    from .batch import Engine, make_params
     _require_cuda()
     h, w = rgb.shape[:2]
+    ch = 1 if rgb.ndim == 2 else 3
     if threshold is None:
         threshold = choose_threshold(w, h)
+    fc = scaled_contrast(contrast_slider) if contrast_slider is not None else 1.0
+    fb = scaled_brightness(brightness_slider) if brightness_slider is not None else 1.0
+    params = make_params(threshold, black_stone_threshold, contrast_factor=fc, brightness_factor=fb)
 
     def run(lim):
         eng = Engine(1, h, w, limits=lim, taps=True)
-        recs = eng.run_host(np.ascontiguousarray(rgb, np.uint8)[None], threshold, black_stone_threshold)
+        recs = eng.run_host(np.ascontiguousarray(rgb, np.uint8)[None], params, channels=ch)
         return (eng, recs), int(recs[0]["status"])
 
     eng, recs = _retrying(run)
     r = recs[0]
+    if int(r["status"]) & N.ST_GRID_OVERFLOW:
+        raise N.NativeError(f"more than {N.MAX_GRID} grid lines on an axis: the fixed-size grid record cannot hold "
+                            "them (the reference reports 'too many lines' above 19, img2sgf.py:568-571)")
     t = eng.taps_host()
     nc = int(t["counts"][0])
     g = t["grids"][0]
@@ -406,13 +442,28 @@ def process_image(rgb: np.ndarray, threshold: int | None = None,
     col = lambda a: [] if len(a) == 0 else a.reshape(-1, 1)
     ready = bool(r["board_ready"])
     full = r["board"].reshape(BOARD_SIZE, BOARD_SIZE).astype(np.float64)
+    circles = t["circles"][0, :nc].copy()
+    kept = circles
+    if g["valid"]:
+        lo, hi = min(g["hspace"], g["vspace"]) * 0.3, max(g["hspace"], g["vspace"]) * 0.65
+        kept = circles[(circles[:, 2] > lo) & (circles[:, 2] < hi)] if nc else circles
+    k = int(r["n_black"]) + int(r["n_white"])
     return Processed(
-        grey_image_np=t["grey"][0], edge_detected_image_np=t["edges"][0], circles=t["circles"][0, :nc].copy(),
+        grey_image_np=t["grey"][0], edge_detected_image_np=t["edges"][0], circles=circles, circles_in_grid=kept,
         circles_removed_image_np=t["masked"][0], hlines=col(t["rho"][0, 0, :lc[0]].copy()),
         vlines=col(t["rho"][0, 1, :lc[1]].copy()), valid_grid=bool(g["valid"]), hsize=hs, vsize=vs,
         hspace=float(g["hspace"]), vspace=float(g["vspace"]),
         hcentres_complete=g["hcentres"][:vs].copy() if g["valid"] else None,
         vcentres_complete=g["vcentres"][:hs].copy() if g["valid"] else None,
         board_ready=ready, detected_board=full[:hs, :vs].copy() if ready else None,
-        full_board=full if ready else None, num_black_stones=int(r["n_black"]), num_white_stones=int(r["n_white"]),
-        record=r)
+        full_board=full if ready else None, stone_brightnesses=t["brightness"][0, :k].copy() if ready else None,
+        num_black_stones=int(r["n_black"]), num_white_stones=int(r["n_white"]), record=r)
+
+
+def process_images(images, line_threshold=None, black_stone_threshold: int = black_stone_threshold_default,
+                   runner=None, **kw) -> np.ndarray:
+    """The batched form of process_image() for images of any sizes: one record per image (board, grid
+    verdict, counts), no image-sized outputs.  See batch.RaggedRunner."""
+    from .batch import RaggedRunner
+    runner = runner or RaggedRunner()
+    return runner.process_images(images, line_threshold, black_stone_threshold, **kw)

@@ -108,21 +108,24 @@ __device__ __forceinline__ void py_slice(int len, int &lo, int &hi)
     if (lo > len) lo = len;
 }
 
-__global__ void __launch_bounds__(512) k_classify(const uint8_t *__restrict__ grey, int h, int w,
-                                                  const float *__restrict__ circles, const int32_t *__restrict__ counts,
-                                                  int circle_cap, const i2s_grid_t *__restrict__ grids, int black_thr,
-                                                  i2s_record_t *records, double *brightness, const int32_t *status)
+// identify_board in three small kernels so that the window means -- the only real work -- spread over
+// the whole machine instead of one block per image:
+//   k_classify_mark : per image, record header + STONE marks from the radius-filtered circles (:441-443, :504-505)
+//   k_classify_mean : one warp per (image, intersection), mean of the clipped half-open window (:468-481)
+//   k_classify_count: per image, stone counts and the brightness list in (i, j) scan order (:506-515)
+__global__ void __launch_bounds__(256) k_classify_mark(const float *__restrict__ circles, const int32_t *__restrict__ counts,
+                                                       int circle_cap, const i2s_grid_t *__restrict__ grids,
+                                                       i2s_record_t *records, const int32_t *status)
 {
-    __shared__ uint8_t s_board[BS * BS];
-    __shared__ double s_mean[BS * BS];
     __shared__ double s_hc[BS], s_vc[BS];
     const int img = blockIdx.x;
     const i2s_grid_t *g = grids + img;
     i2s_record_t *rec = records + img;
     const int ncirc = min(counts[img], circle_cap);
     const bool ready = g->valid && g->hsize <= BS && g->vsize <= BS;
-    uint8_t *recb = reinterpret_cast<uint8_t *>(rec);
-    for (int i = threadIdx.x; i < (int)sizeof(i2s_record_t); i += blockDim.x) recb[i] = 0;
+    uint32_t *recw = reinterpret_cast<uint32_t *>(rec);
+    for (int i = threadIdx.x; i < (int)sizeof(i2s_record_t) / 4; i += blockDim.x) recw[i] = 0;
+    if (ready && threadIdx.x < BS) { s_hc[threadIdx.x] = g->hcentres[threadIdx.x]; s_vc[threadIdx.x] = g->vcentres[threadIdx.x]; }
     __syncthreads();
     if (threadIdx.x == 0) {
         rec->valid = (uint8_t)(g->valid != 0);
@@ -135,9 +138,6 @@ __global__ void __launch_bounds__(512) k_classify(const uint8_t *__restrict__ gr
     if (!ready) return;
     const int hs = g->hsize, vs = g->vsize;
     const double hspace = g->hspace, vspace = g->vspace;
-    for (int i = threadIdx.x; i < BS * BS; i += blockDim.x) { s_board[i] = 0; s_mean[i] = 0.0; }
-    if (threadIdx.x < BS) { s_hc[threadIdx.x] = g->hcentres[threadIdx.x]; s_vc[threadIdx.x] = g->vcentres[threadIdx.x]; }
-    __syncthreads();
     // validate_grid's radius filter (:441-443) then nearest-intersection snap (:504-505)
     const double lo = fmin(hspace, vspace) * 0.3, hi = fmax(hspace, vspace) * 0.65;
     const float *circ = circles + (size_t)img * circle_cap * 3;
@@ -146,55 +146,82 @@ __global__ void __launch_bounds__(512) k_classify(const uint8_t *__restrict__ gr
         if (!(lo < r && r < hi)) continue;
         int i = closest_index((double)circ[3 * c], s_vc, hs);
         int j = closest_index((double)circ[3 * c + 1], s_hc, vs);
-        s_board[i * vs + j] = 3;
+        rec->board[i * BS + j] = 3;
     }
-    __syncthreads();
-    // one warp per stone: mean of the clipped half-open window (:468-481)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint8_t *gimg = grey + (size_t)img * h * w;
-    for (int cell = warp; cell < hs * vs; cell += blockDim.x >> 5) {
-        if (s_board[cell] != 3) continue;
-        int i = cell / vs, j = cell - i * vs;
-        double x = s_vc[i], y = s_hc[j];
-        int xmin = (int)rint(x - hspace / 2), xmax = (int)rint(x + hspace / 2);
-        int ymin = (int)rint(y - vspace / 2), ymax = (int)rint(y + vspace / 2);
-        xmin = max(0, xmin); ymin = max(0, ymin);
-        xmax = min(w, xmax); ymax = min(h, ymax);
-        py_slice(w, xmin, xmax);
-        py_slice(h, ymin, ymax);
-        const int ww = xmax - xmin, wh = ymax - ymin;
-        unsigned long long sum = 0;
-        if (ww > 0 && wh > 0) {
-            const int tot = ww * wh;
-            for (int p = lane; p < tot; p += 32) {
-                int py = p / ww, px = p - py * ww;
-                sum += __ldg(gimg + (size_t)(ymin + py) * w + xmin + px);
-            }
+}
+
+constexpr int CM_WARPS = 8;
+
+__global__ void __launch_bounds__(CM_WARPS * 32) k_classify_mean(const uint8_t *__restrict__ grey, int pitch, size_t stride,
+                                                                const Dims dims, int n, const i2s_grid_t *__restrict__ grids,
+                                                                int black_thr, i2s_record_t *records, double *brightness)
+{
+    const int lane = threadIdx.x & 31;
+    const int item = blockIdx.x * CM_WARPS + (threadIdx.x >> 5);          // (image, intersection)
+    if (item >= n * BS * BS) return;
+    const int img = item / (BS * BS), cell = item - img * (BS * BS);
+    i2s_record_t *rec = records + img;
+    if (rec->board[cell] != 3) return;                                    // warp-uniform
+    const int i = cell / BS, j = cell - i * BS;
+    const i2s_grid_t *g = grids + img;
+    const int2 wh = dims.of(img);
+    const int w = wh.x, h = wh.y;
+    const double hspace = g->hspace, vspace = g->vspace;
+    const double x = g->vcentres[i], y = g->hcentres[j];
+    int xmin = (int)rint(x - hspace / 2), xmax = (int)rint(x + hspace / 2);
+    int ymin = (int)rint(y - vspace / 2), ymax = (int)rint(y + vspace / 2);
+    xmin = max(0, xmin); ymin = max(0, ymin);
+    xmax = min(w, xmax); ymax = min(h, ymax);
+    py_slice(w, xmin, xmax);
+    py_slice(h, ymin, ymax);
+    const int ww = xmax - xmin, wh_ = ymax - ymin;
+    unsigned int sum = 0;                                                  // <= 255 * 16384^2 would overflow; windows are < 2^23 px
+    unsigned long long sum64 = 0;
+    if (ww > 0 && wh_ > 0) {
+        const uint8_t *base = grey + img * stride + (size_t)ymin * pitch + xmin;
+        for (int py = 0; py < wh_; py++) {
+            const uint8_t *row = base + (size_t)py * pitch;
+            for (int px = lane; px < ww; px += 32) sum += __ldg(row + px);
+            if ((py & 255) == 255) { sum64 += sum; sum = 0; }
         }
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
-        if (lane == 0) {
-            double mean = (ww > 0 && wh > 0) ? (double)sum / (double)((long long)ww * wh) : nan("");
-            s_mean[cell] = mean;
-            s_board[cell] = (mean <= (double)black_thr) ? 1 : 2;     // NaN -> WHITE, like the reference
-        }
+        sum64 += sum;
     }
-    __syncthreads();
-    for (int c = threadIdx.x; c < hs * vs; c += blockDim.x) {
-        int i = c / vs, j = c - i * vs;
-        rec->board[i * BS + j] = s_board[c];
+    for (int o = 16; o > 0; o >>= 1) sum64 += __shfl_down_sync(0xffffffffu, sum64, o);
+    if (lane == 0) {
+        const double mean = (ww > 0 && wh_ > 0) ? (double)sum64 / (double)((long long)ww * wh_) : nan("");
+        if (brightness) brightness[(size_t)img * BS * BS + cell] = mean;
+        rec->board[cell] = (mean <= (double)black_thr) ? 1 : 2;          // NaN -> WHITE, like the reference
     }
-    if (threadIdx.x == 0) {
-        int k = 0, nb = 0, nw = 0;
-        double *br = brightness ? brightness + (size_t)img * BS * BS : nullptr;
-        for (int c = 0; c < hs * vs; c++) {
-            if (!s_board[c]) continue;
-            if (br) br[k] = s_mean[c];
-            k++;
-            if (s_board[c] == 1) nb++; else nw++;
-        }
-        if (br) for (; k < BS * BS; k++) br[k] = 0.0;
-        rec->n_black = nb; rec->n_white = nw;
+}
+
+__global__ void __launch_bounds__(32) k_classify_count(i2s_record_t *records, double *brightness)
+{
+    const int img = blockIdx.x, lane = threadIdx.x;
+    i2s_record_t *rec = records + img;
+    if (!rec->board_ready) {
+        if (brightness)
+            for (int c = lane; c < BS * BS; c += 32) brightness[(size_t)img * BS * BS + c] = 0.0;
+        return;
     }
+    // cells in (i, j) scan order = ascending board index; ballot keeps the order
+    int nb = 0, nw = 0, k = 0;
+    double *br = brightness ? brightness + (size_t)img * BS * BS : nullptr;
+    for (int c0 = 0; c0 < BS * BS; c0 += 32) {
+        const int c = c0 + lane;
+        const int v = c < BS * BS ? rec->board[c] : 0;
+        const double m = (br && v) ? br[c] : 0.0;
+        const uint32_t stones = __ballot_sync(0xffffffffu, v != 0);
+        nb += __popc(__ballot_sync(0xffffffffu, v == 1));
+        nw += __popc(__ballot_sync(0xffffffffu, v == 2));
+        __syncwarp();
+        // forward compaction in place: the destination index never exceeds the source index
+        if (br && v) br[k + __popc(stones & ((1u << lane) - 1u))] = m;
+        k += __popc(stones);
+        __syncwarp();
+    }
+    if (br)
+        for (int c = k + lane; c < BS * BS; c += 32) br[c] = 0.0;
+    if (lane == 0) { rec->n_black = nb; rec->n_white = nw; }
 }
 
 int validate_grid(const double *centres, const int32_t *ncentres, int n, int line_cap, i2s_grid_t *grids,
@@ -206,14 +233,18 @@ int validate_grid(const double *centres, const int32_t *ncentres, int n, int lin
     return I2S_OK;
 }
 
-int classify_stones(const uint8_t *grey, int n, int h, int w, const float *circles, const int32_t *counts,
-                    int circle_cap, const i2s_grid_t *grids, int black_threshold, i2s_record_t *records,
-                    double *brightness, const int32_t *status, cudaStream_t st)
+int classify_stones(const uint8_t *grey, const Dims &dims, int n, int pitch, size_t stride, const float *circles,
+                    const int32_t *counts, int circle_cap, const i2s_grid_t *grids, int black_threshold,
+                    i2s_record_t *records, double *brightness, const int32_t *status, cudaStream_t st)
 {
     ScopedSection sec(SEC_CLASSIFY, st);
-    k_classify<<<n, 512, 0, st>>>(grey, h, w, circles, counts, circle_cap, grids, black_threshold, records, brightness,
-                                  status);
-    I2S_CHECK_LAUNCH("k_classify");
+    k_classify_mark<<<n, 256, 0, st>>>(circles, counts, circle_cap, grids, records, status);
+    I2S_CHECK_LAUNCH("k_classify_mark");
+    k_classify_mean<<<cdiv(n * BS * BS, CM_WARPS), CM_WARPS * 32, 0, st>>>(grey, pitch, stride, dims, n, grids, black_threshold,
+                                                                         records, brightness);
+    I2S_CHECK_LAUNCH("k_classify_mean");
+    k_classify_count<<<n, 32, 0, st>>>(records, brightness);
+    I2S_CHECK_LAUNCH("k_classify_count");
     return I2S_OK;
 }
 
@@ -229,12 +260,14 @@ extern "C" int i2s_validate_grid(const double *centres, const int32_t *ncentres,
     return validate_grid(centres, ncentres, n, line_cap, grids, status, (cudaStream_t)stream);
 }
 
-extern "C" int i2s_classify_stones(const uint8_t *grey, int n, int h, int w, const float *circles, const int32_t *counts,
-                                   int circle_cap, const i2s_grid_t *grids, int black_threshold, i2s_record_t *records,
-                                   double *brightness, void *stream)
+extern "C" int i2s_classify_stones(const uint8_t *grey, int pitch, int n, int h, int w, const float *circles,
+                                   const int32_t *counts, int circle_cap, const i2s_grid_t *grids, int black_threshold,
+                                   i2s_record_t *records, double *brightness, void *stream)
 {
     I2S_ARG(grey && circles && counts && grids && records && n >= 0 && h > 0 && w > 0 && circle_cap > 0);
+    if (pitch == 0) pitch = w;
+    I2S_ARG(pitch >= w);
     if (n == 0) return I2S_OK;
-    return classify_stones(grey, n, h, w, circles, counts, circle_cap, grids, black_threshold, records, brightness,
-                           nullptr, (cudaStream_t)stream);
+    return classify_stones(grey, Dims::uniform(h, w), n, pitch, (size_t)h * pitch, circles, counts, circle_cap, grids,
+                           black_threshold, records, brightness, nullptr, (cudaStream_t)stream);
 }

@@ -4,189 +4,106 @@
 // (integer votes; float32 step vectors / distances / radius scoring with IEEE rn ops).
 #include "canny.cuh"
 #include "circles.cuh"
+#include "preproc.cuh"
 #include "sort.cuh"
 #include "profile.cuh"
 
 namespace i2s {
 
-constexpr int MIN_R = 1, MAX_R = 30, ACC_THR = 30, NBINS = 290;
+constexpr int MAX_R = 30, ACC_THR = 30, NBINS = 290;      // minRadius 1: radii 1..30 are |t| of the signed radius t != 0
 constexpr int CANNY_LOW = 50, CANNY_HIGH = 100;
 
 // ------------------------------------------------------------------ K5a: edge lists
 // The edge pixels of every map are compacted once into a global list of (position, Q10 gradient
-// step), bucketed by 32x32 pixel tile: one block scans its tile of the state map (ballot
-// compaction, no per-pixel atomics), reserves a contiguous slice of the map's list with a single
-// atomic, recomputes the Sobel gradient of each edge pixel from the source image and stores
-// sx = cvRound(dx*1024/mag), sy likewise.  Order inside a bucket is arbitrary;
-// votes commute.
+// step), bucketed by 32x32 pixel tile.  One WARP owns one bucket: two 128-bit loads per lane fetch
+// its state bytes, the edge bits are squeezed into a 32-bit mask per lane, one shuffle scan gives
+// every lane its slot, lane 0 reserves the bucket's slice of the map's list with a single atomic
+// and publishes the directory entry.  The positions go through a per-warp shared-memory list so
+// that the expensive part -- recomputing the Sobel gradient of each edge pixel from the source image
+// and sx = cvRound(dx*1024/mag), sy likewise -- runs with all lanes busy.
+// No block-wide barrier.  Order inside a bucket is arbitrary; votes commute.
 constexpr int EB = 32;
+constexpr int EL_WARPS = 8;
 
-__device__ __forceinline__ void sobel_at(const uint8_t *__restrict__ img, int h, int w, int x, int y, int &dx,
-                                         int &dy)
-{
-    int xm = x > 0 ? x - 1 : 0, xp = x < w - 1 ? x + 1 : w - 1;
-    const uint8_t *r0 = img + (size_t)(y > 0 ? y - 1 : 0) * w;
-    const uint8_t *r1 = img + (size_t)y * w;
-    const uint8_t *r2 = img + (size_t)(y < h - 1 ? y + 1 : h - 1) * w;
-    int p00 = __ldg(r0 + xm), p01 = __ldg(r0 + x), p02 = __ldg(r0 + xp);
-    int p10 = __ldg(r1 + xm), p12 = __ldg(r1 + xp);
-    int p20 = __ldg(r2 + xm), p21 = __ldg(r2 + x), p22 = __ldg(r2 + xp);
-    dx = (p02 + 2 * p12 + p22) - (p00 + 2 * p10 + p20);
-    dy = (p20 + 2 * p21 + p22) - (p00 + 2 * p01 + p02);
-}
+__device__ __forceinline__ uint32_t edge_nibble(uint32_t v) { return (((v >> 1) & 0x01010101u) * 0x01020408u) >> 24; }
 
-// Second phase shared by both compaction kernels: reserve a slice of the map's list per bucket,
-// publish the directory entry, then recompute the Sobel gradient of every compacted edge pixel
-// and store (position, Q10 step).
-__device__ __forceinline__ void edge_emit(const uint8_t *__restrict__ img, int h, int w, int map, size_t plane,
-                                          uint32_t (*s_pos)[EB * EB], int *s_n, int *s_off, int *s_end,
-                                          uint2 *__restrict__ edges, int32_t *ecount, int2 *dir, int nbx, int nby)
+__global__ void __launch_bounds__(EL_WARPS * 32) k_edge_list(const MapSet ms, const Dims dims, const uint8_t *__restrict__ state,
+                                                            int spitch, size_t sstride, uint2 *__restrict__ edges, size_t estride,
+                                                            int32_t *ecount, int2 *dir, int nbx, int nby)
 {
-    __syncthreads();
-    if (threadIdx.x < 4) {
-        const int sub = threadIdx.x;
-        const int bxx = blockIdx.x * 2 + (sub & 1), byy = blockIdx.y * 2 + (sub >> 1);
-        const int n = s_n[sub];
-        int off = 0;
-        if (bxx < nbx && byy < nby) {
-            off = n ? atomicAdd(ecount + map, n) : 0;
-            dir[((size_t)map * nby + byy) * nbx + bxx] = make_int2(off, n);
+    __shared__ uint16_t s_pos[EL_WARPS][EB * EB];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int map = blockIdx.z, by = blockIdx.y, bx = blockIdx.x * EL_WARPS + warp;
+    if (bx >= nbx) return;                                       // warp-uniform from here on
+    const int2 wh = dims.of(map % ms.n);
+    const int w = wh.x, h = wh.y;
+    if (bx * EB >= w || by * EB >= h) return;                    // bucket outside this image: never read by anyone
+    const uint8_t *stm = state + map * sstride;
+    // state bytes of the bucket: lane -> 16 pixels of row (lane >> 1) [+16 in the second pass]
+    const int x = bx * EB + 16 * (lane & 1);
+    uint32_t M = 0;                                              // bit 16*pass + j: pixel (x + j, row)
+#pragma unroll
+    for (int pass = 0; pass < 2; pass++) {
+        const int y = by * EB + 16 * pass + (lane >> 1);
+        if (y < h && x < w) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(stm + (size_t)y * spitch + x));
+            uint32_t m16 = edge_nibble(v.x) | (edge_nibble(v.y) << 4) | (edge_nibble(v.z) << 8) | (edge_nibble(v.w) << 12);
+            if (w - x < 16) m16 &= (1u << (w - x)) - 1u;        // columns beyond the image
+            M |= m16 << (16 * pass);
         }
-        s_off[sub] = off;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        s_end[0] = 0;
-        for (int k = 0; k < 4; k++) s_end[k + 1] = s_end[k] + s_n[k];
+    const int c = __popc(M);
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
     }
-    __syncthreads();
-    uint2 *out = edges + (size_t)map * plane;
-    const int total = s_end[4];
-    int sub = 0;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        while (i >= s_end[sub + 1]) sub++;
-        const int li = i - s_end[sub];
-        const uint32_t e = s_pos[sub][li];
-        const int x = e & 0xffff, y = e >> 16;
-        int dx, dy;
-        sobel_at(img, h, w, x, y, dx, dy);
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int off = 0;
+    if (lane == 0) {
+        off = total ? atomicAdd(ecount + map, total) : 0;
+        dir[((size_t)map * nby + by) * nbx + bx] = make_int2(off, total);
+    }
+    if (total == 0) return;
+    off = __shfl_sync(0xffffffffu, off, 0);
+    uint16_t *lst = s_pos[warp];
+    {
+        int p = incl - c;
+        uint32_t m = M;
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            lst[p++] = (uint16_t)((((b & 16) + (lane >> 1)) << 5) | (((lane & 1) << 4) + (b & 15)));
+        }
+    }
+    __syncwarp();
+    int ipitch;
+    const uint8_t *img = ms.plane(map, ipitch);
+    uint2 *out = edges + map * estride + off;
+    for (int i = lane; i < total; i += 32) {
+        const int pos = lst[i];
+        const int px = bx * EB + (pos & 31), py = by * EB + (pos >> 5);
+        // Sobel 3x3, replicate border (A.4)
+        const uint32_t xm = (uint32_t)max(px - 1, 0), xp = (uint32_t)min(px + 1, w - 1);
+        const uint32_t o0 = (uint32_t)max(py - 1, 0) * (uint32_t)ipitch, o1 = (uint32_t)py * (uint32_t)ipitch,
+                       o2 = (uint32_t)min(py + 1, h - 1) * (uint32_t)ipitch;
+        const int p00 = __ldg(img + o0 + xm), p01 = __ldg(img + o0 + px), p02 = __ldg(img + o0 + xp);
+        const int p10 = __ldg(img + o1 + xm), p12 = __ldg(img + o1 + xp);
+        const int p20 = __ldg(img + o2 + xm), p21 = __ldg(img + o2 + px), p22 = __ldg(img + o2 + xp);
+        const int dx = (p02 + 2 * p12 + p22) - (p00 + 2 * p10 + p20);
+        const int dy = (p20 + 2 * p21 + p22) - (p00 + 2 * p01 + p02);
         int sx = 0, sy = 0;
         if (dx != 0 || dy != 0) {
-            float vx = (float)dx, vy = (float)dy;
-            float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)));
+            const float vx = (float)dx, vy = (float)dy;
+            const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)));
             if (!(mag < 1.0f)) {
                 sx = __float2int_rn(__fdiv_rn(__fmul_rn(vx, 1024.0f), mag));
                 sy = __float2int_rn(__fdiv_rn(__fmul_rn(vy, 1024.0f), mag));
             }
         }
-        out[s_off[sub] + li] = make_uint2(e, (uint32_t)(sx & 0xffff) | ((uint32_t)sy << 16));   // (0,0) step = no vote
+        out[i] = make_uint2(((uint32_t)py << 16) | (uint32_t)px, (uint32_t)(sx & 0xffff) | ((uint32_t)sy << 16));   // (0,0) step = no vote
     }
-}
-
-__global__ void __launch_bounds__(256) k_edge_buckets(const MapSet ms, const uint8_t *__restrict__ state, int h, int w,
-                                                      bool al, uint2 *__restrict__ edges, int32_t *ecount, int2 *dir,
-                                                      int nbx, int nby)
-{
-    // one block compacts a 2x2 group of buckets (64x64 pixels)
-    __shared__ uint32_t s_pos[4][EB * EB];
-    __shared__ int s_n[4], s_off[4], s_end[5];
-    static_assert(EB * (EB / 4) == 256, "one 32-bit word of a bucket's state tile per thread");
-    const size_t plane = (size_t)h * w;
-    const int map = blockIdx.z;
-    const uint8_t *img = ms.plane(map, plane);
-    const uint8_t *stm = state + map * plane;
-    const int lane = threadIdx.x & 31;
-    if (threadIdx.x < 4) s_n[threadIdx.x] = 0;
-    __syncthreads();
-    // all four state words of this thread first (independent loads in flight), then the compaction
-    uint32_t vv[4];
-#pragma unroll
-    for (int sub = 0; sub < 4; sub++) {
-        const int bxx = blockIdx.x * 2 + (sub & 1), byy = blockIdx.y * 2 + (sub >> 1);
-        const int ty = threadIdx.x / (EB / 4), gx = (threadIdx.x % (EB / 4)) * 4;
-        const int y = byy * EB + ty, x = bxx * EB + gx;
-        uint32_t v = 0;
-        if (bxx < nbx && byy < nby && y < h && x < w) {
-            const uint8_t *p = stm + (size_t)y * w + x;
-            if (al && x + 3 < w) v = __ldg(reinterpret_cast<const uint32_t *>(p));
-            else
-                for (int k = 0; k < 4 && x + k < w; k++) v |= (uint32_t)__ldg(p + k) << (8 * k);
-        }
-        vv[sub] = v;
-    }
-#pragma unroll
-    for (int sub = 0; sub < 4; sub++) {
-        const int bxx = blockIdx.x * 2 + (sub & 1), byy = blockIdx.y * 2 + (sub >> 1);
-        if (bxx >= nbx || byy >= nby) continue;                      // block-uniform
-        const int ty = threadIdx.x / (EB / 4), gx = (threadIdx.x % (EB / 4)) * 4;
-        const int y = byy * EB + ty, x = bxx * EB + gx;
-        uint32_t v = vv[sub];
-        v &= 0x02020202u;
-        const int nb = __popc(v);                                    // 0..4 edge pixels in this word
-        const uint32_t b0 = __ballot_sync(0xffffffffu, nb & 1), b1 = __ballot_sync(0xffffffffu, nb & 2),
-                       b2 = __ballot_sync(0xffffffffu, nb & 4);
-        const uint32_t lt = (1u << lane) - 1u;
-        const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
-        int base = 0;
-        if (lane == 0 && total) base = atomicAdd(&s_n[sub], total);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        int pos = base + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
-        while (v) {
-            int k = (__ffs(v) - 1) >> 3;
-            v &= ~(0xffu << (8 * k));
-            s_pos[sub][pos++] = ((uint32_t)y << 16) | (uint32_t)(x + k);
-        }
-    }
-    edge_emit(img, h, w, map, plane, s_pos, s_n, s_off, s_end, edges, ecount, dir, nbx, nby);
-}
-
-// Same result with 16 pixels (one 128-bit load) per thread: thread t owns row t/4 and the 16-pixel
-// column group t%4 of the block's 64x64 pixels, so a warp covers 8 rows of two buckets (lanes with
-// the same bit 1 share a bucket) and needs one 5-bit ballot prefix per 16 pixels instead of one
-// 3-bit prefix per 4.  Requires w % 16 == 0 and a 16-byte aligned state map.
-__global__ void __launch_bounds__(256) k_edge_buckets16(const MapSet ms, const uint8_t *__restrict__ state, int h, int w,
-                                                        uint2 *__restrict__ edges, int32_t *ecount, int2 *dir,
-                                                        int nbx, int nby)
-{
-    __shared__ uint32_t s_pos[4][EB * EB];
-    __shared__ int s_n[4], s_off[4], s_end[5];
-    const size_t plane = (size_t)h * w;
-    const int map = blockIdx.z;
-    const uint8_t *img = ms.plane(map, plane);
-    const uint8_t *stm = state + map * plane;
-    const int lane = threadIdx.x & 31;
-    const int row = threadIdx.x >> 2, cg = threadIdx.x & 3;
-    const int y = blockIdx.y * (2 * EB) + row, x = blockIdx.x * (2 * EB) + cg * 16;
-    const int sub = (row >> 5) * 2 + (cg >> 1);
-    if (threadIdx.x < 4) s_n[threadIdx.x] = 0;
-    __syncthreads();
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (y < h && x < w) v = __ldg(reinterpret_cast<const uint4 *>(stm + (size_t)y * w + x));
-    uint32_t wd[4] = {v.x & 0x02020202u, v.y & 0x02020202u, v.z & 0x02020202u, v.w & 0x02020202u};
-    const int nbits = __popc(wd[0]) + __popc(wd[1]) + __popc(wd[2]) + __popc(wd[3]);      // 0..16
-    const uint32_t bm = (lane & 2) ? 0xccccccccu : 0x33333333u;                            // lanes of my bucket
-    const uint32_t lt = ((1u << lane) - 1u) & bm;
-    int pre = 0, tot = 0;
-#pragma unroll
-    for (int k = 0; k < 5; k++) {
-        const uint32_t b = __ballot_sync(0xffffffffu, (nbits >> k) & 1);
-        pre += __popc(b & lt) << k;
-        tot += __popc(b & bm) << k;
-    }
-    int base = 0;
-    if ((lane == 0 || lane == 2) && tot) base = atomicAdd(&s_n[sub], tot);
-    base = __shfl_sync(0xffffffffu, base, lane & 2);
-    int pos = base + pre;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        uint32_t m = wd[k];
-        while (m) {
-            const int j = (__ffs(m) - 1) >> 3;
-            m &= m - 1;
-            s_pos[sub][pos++] = ((uint32_t)y << 16) | (uint32_t)(x + 4 * k + j);
-        }
-    }
-    edge_emit(img, h, w, map, plane, s_pos, s_n, s_off, s_end, edges, ecount, dir, nbx, nby);
 }
 
 // ------------------------------------------------------------------ K5+K6: voting fused with peak finding
@@ -199,6 +116,17 @@ __global__ void __launch_bounds__(256) k_edge_buckets16(const MapSet ms, const u
 // with no bounds test.  Rays are monotone in x and y, hence "cells inside the tile" is one interval
 // of radii and dropping out-of-image cells equals the reference's break.  Votes are integers, so
 // the result does not depend on the order of the atomics.
+//
+// Every warp owns one contiguous slice of the tile's item sequence (lanes interleaved), so the bucket
+// pointer moves by a step or two per iteration after one binary search per warp.
+//
+// The vote loop.  The reference's cell for signed radius t is ((x<<10) + t*sx) >> 10 = x + floor(t*sx/1024)
+// (x is an integer), so the OFFSET of the cell from the pixel depends on (t, sx, sy) only.  Both offsets
+// travel in one register: U(t) = (t*sy + 2^15) << 16 | (t*sx + 2^15) = 0x80008000 + t*S with S = sy*65536 + sx;
+// |t*s| <= 30*1024 keeps each half inside its 16 bits, so a single 32-bit add steps both coordinates.
+// Bits 10..15 of each half are floor(t*s/1024) + 32; (U >> 8) & 0x00FC00FC holds four times those two
+// numbers in its 16-bit halves, and one 16-bit x 8-bit dot product (IDP.2A) with the byte pair
+// (1, pitch) turns that into the byte address of the cell.  Per vote: add, shift, and, dot, atomic.
 constexpr int AT = 128;                      // tile edge in accumulator cells
 constexpr int AG = 2;                        // guard cells around the ring
 constexpr int AS = AT + 2 + 2 * AG;          // shared rows / used columns
@@ -206,115 +134,16 @@ constexpr int AP = AS + 1;                   // shared pitch (odd: column walks 
 constexpr int VOTE_THREADS = 512;
 constexpr int VOTE_SMEM = AS * AP * 4;
 constexpr int VB = 7;                        // buckets per axis that can overlap a tile's region
+static_assert(AP < 256, "the pitch is a byte operand of the address dot product");
 
-__global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks(const uint2 *__restrict__ edges,
-                                                             const int2 *__restrict__ dir, int nbx, int nby, int h,
-                                                             int w, int32_t *cand, int32_t *ncand, int cand_cap)
+__device__ __forceinline__ void vote_at(uint32_t a0, uint32_t U)
 {
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    int *s_acc = reinterpret_cast<int *>(s_raw);                       // AS x AP
-    __shared__ int s_boff[VB * VB], s_bend[VB * VB + 1];               // bucket slice start / running item end
-    const size_t plane = (size_t)h * w;
-    const int map = blockIdx.z;
-    const uint2 *elist = edges + map * plane;
-    const int tx0 = blockIdx.x * AT, ty0 = blockIdx.y * AT;      // first cell of the tile proper
-    const int cx0 = tx0 - 1 - AG, cy0 = ty0 - 1 - AG;            // cell coordinates of shared (0,0)
-    // cells of the ring that exist in the image: the clip box of the rays
-    const int X0 = max(tx0 - 1, 0), X1 = min(tx0 + AT, w - 1);
-    const int Y0 = max(ty0 - 1, 0), Y1 = min(ty0 + AT, h - 1);
-    // pixels that can reach the ring, and the buckets holding them
-    const int rx0 = max(tx0 - 1 - MAX_R, 0), rx1 = min(tx0 + AT + MAX_R, w - 1);
-    const int ry0 = max(ty0 - 1 - MAX_R, 0), ry1 = min(ty0 + AT + MAX_R, h - 1);
-    const int bx0 = rx0 / EB, bx1 = rx1 / EB, by0 = ry0 / EB, by1 = ry1 / EB;
-    const int nbw = bx1 - bx0 + 1, nb = nbw * (by1 - by0 + 1);      // <= VB*VB
-    for (int i = threadIdx.x; i < AS * AP; i += blockDim.x) s_acc[i] = 0;
-    if (threadIdx.x < nb) {
-        int b = threadIdx.x;
-        int2 d = dir[((size_t)map * nby + by0 + b / nbw) * nbx + bx0 + b % nbw];
-        s_boff[b] = d.x;
-        s_bend[b + 1] = d.y;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int run = 0;
-        s_bend[0] = 0;
-        for (int b = 0; b < nb; b++) { run += s_bend[b + 1]; s_bend[b + 1] = run; }
-    }
-    __syncthreads();
-    const int items = s_bend[nb];                                   // one item = one edge pixel, both rays
-    int b = 0;
-    for (int it = threadIdx.x; it < items; it += blockDim.x) {
-        while (it >= s_bend[b + 1]) b++;                             // `it` only grows: b is monotone
-        const uint2 e = __ldg(elist + s_boff[b] + (it - s_bend[b]));
-        const int x = e.x & 0xffff, y = e.x >> 16;
-        if (x < rx0 || x > rx1 || y < ry0 || y > ry1) continue;
-        const int sx = (int)(short)(e.y & 0xffff), sy = (int)e.y >> 16;
-        if (sx == 0 && sy == 0) continue;
-        // Signed radii t (cell = pixel + t * step, t in [-30,-1] U [1,30]) whose cell lies in
-        // [X0,X1] x [Y0,Y1]: one interval [lo,hi] in float, conservative by < 1 step each side.
-        float lo = -(float)MAX_R, hi = (float)MAX_R;
-        if (sx != 0) {
-            float inv = __fdividef(1024.0f, (float)sx);
-            float ta = (float)(X0 - x) * inv, tb = (float)(X1 + 1 - x) * inv;
-            lo = fmaxf(lo, fminf(ta, tb)); hi = fminf(hi, fmaxf(ta, tb));
-        } else if (x < X0 || x > X1) continue;
-        if (sy != 0) {
-            float inv = __fdividef(1024.0f, (float)sy);
-            float ta = (float)(Y0 - y) * inv, tb = (float)(Y1 + 1 - y) * inv;
-            lo = fmaxf(lo, fminf(ta, tb)); hi = fminf(hi, fmaxf(ta, tb));
-        } else if (y < Y0 || y > Y1) continue;
-        // 0.25 of slack covers the error of the approximate divide; at most one extra step per side
-        const int t_lo = max(-MAX_R, (int)floorf(lo - 0.25f)), t_hi = min(MAX_R, (int)ceilf(hi + 0.25f));
-        const int xb = (x - cx0) * 1024, yb = (y - cy0) * 1024;
-        {   // forward ray: t = max(t_lo,1) .. t_hi
-            const int r0 = max(t_lo, MIN_R);
-            int x1 = xb + r0 * sx, y1 = yb + r0 * sy;
-#pragma unroll 4
-            for (int r = r0; r <= t_hi; r++, x1 += sx, y1 += sy)
-                atomicAdd(s_acc + (y1 >> 10) * AP + (x1 >> 10), 1);
-        }
-        {   // backward ray: t = -1 down to t_lo, i.e. radius r = -t
-            const int r0 = max(-t_hi, MIN_R), r1 = -t_lo;
-            int x1 = xb - r0 * sx, y1 = yb - r0 * sy;
-#pragma unroll 4
-            for (int r = r0; r <= r1; r++, x1 -= sx, y1 -= sy)
-                atomicAdd(s_acc + (y1 >> 10) * AP + (x1 >> 10), 1);
-        }
-    }
-    __syncthreads();
-    // cells outside the image never receive votes in the reference: clear what the conservative
-    // extra steps may have left there (border tiles only)
-    if (cx0 < 0 || cy0 < 0 || cx0 + AS > w || cy0 + AS > h) {
-        for (int i = threadIdx.x; i < AS * AS; i += blockDim.x) {
-            int ly = i / AS, lx = i - ly * AS;
-            int cx = cx0 + lx, cy = cy0 + ly;
-            if (cx < 0 || cy < 0 || cx >= w || cy >= h) s_acc[ly * AP + lx] = 0;
-        }
-        __syncthreads();
-    }
-    // K6: 4-neighbour peaks above the accumulator threshold, interior cells only (x,y >= 1)
-    const int aw = w + 2;
-    for (int idx = threadIdx.x; idx < AT * AT; idx += blockDim.x) {
-        int ty = idx / AT, tx = idx - ty * AT;
-        int cx = tx0 + tx, cy = ty0 + ty;
-        if (cx < 1 || cy < 1 || cx >= w || cy >= h) continue;    // cells x==w / y==h never receive votes
-        const int *c = s_acc + (ty + 1 + AG) * AP + tx + 1 + AG;
-        int v = c[0];
-        if (v > ACC_THR && v > c[-1] && v >= c[1] && v > c[-AP] && v >= c[AP]) {
-            int slot = atomicAdd(ncand + map, 1);
-            if (slot < cand_cap) cand[(size_t)map * cand_cap + slot] = cy * aw + cx;
-        }
-    }
+    const uint32_t m = (U >> 8) & 0x00FC00FCu;
+    const uint32_t addr = __dp2a_lo(m, 1u | ((uint32_t)AP << 8), a0);
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
 }
 
-// ---- second generation of the same kernel -------------------------------------------------------
-// Same tile, same clipping, same atomics.  What changed: every warp owns one contiguous slice of the
-// tile's item sequence (lanes interleaved), so the bucket pointer moves by a step or two per
-// iteration after one binary search per warp, consecutive lanes hold consecutive contour pixels
-// (similar ray lengths, neighbouring banks), and the peak scan reads rows with lane-consecutive
-// columns, testing the threshold before anything else.
-template <int UNROLL>
-__device__ __forceinline__ void vote_item(int *s_acc, uint2 e, int cx0, int cy0, int X0, int X1, int Y0, int Y1)
+__device__ __forceinline__ void vote_item(int *s_acc, uint32_t s_base, uint2 e, int cx0, int cy0, int X0, int X1, int Y0, int Y1)
 {
     const int x = e.x & 0xffff, y = e.x >> 16;
     const int sx = (int)(short)(e.y & 0xffff), sy = (int)e.y >> 16;
@@ -329,33 +158,42 @@ __device__ __forceinline__ void vote_item(int *s_acc, uint2 e, int cx0, int cy0,
         float ta = (float)(Y0 - y) * inv, tb = (float)(Y1 + 1 - y) * inv;
         lo = fmaxf(lo, fminf(ta, tb)); hi = fminf(hi, fmaxf(ta, tb));
     } else if (y < Y0 || y > Y1) return;
+    // 0.25 of slack covers the error of the approximate divide; at most one extra step per side
     const int t_lo = max(-MAX_R, (int)floorf(lo - 0.25f)), t_hi = min(MAX_R, (int)ceilf(hi + 0.25f));
     if (t_lo > t_hi) return;
-    // Both rays are one arithmetic sequence in the signed radius t: cell(t) = floor((p*1024 + t*step) / 1024)
-    // for t > 0 (forward) and t < 0 (backward, r = -t).  One loop over t_lo..t_hi votes them all -- a warp
-    // then runs max(len) instead of max(forward) + max(backward) -- and the vote the loop casts at t = 0
-    // (the pixel's own cell, which the reference never votes) is taken back afterwards.
-    const int xb = (x - cx0) * 1024, yb = (y - cy0) * 1024;
-    int x1 = xb + t_lo * sx, y1 = yb + t_lo * sy;
-#pragma unroll UNROLL
-    for (int t = t_lo; t <= t_hi; t++, x1 += sx, y1 += sy) atomicAdd(s_acc + (y1 >> 10) * AP + (x1 >> 10), 1);
+    // Both rays are one arithmetic sequence in the signed radius t (forward t > 0, backward t < 0, r = |t|).
+    // One loop over t_lo..t_hi votes them all -- a warp then runs max(len) instead of max(forward) +
+    // max(backward) -- and the vote the loop casts at t = 0 (the pixel's own cell, which the reference
+    // never votes) is taken back afterwards.
+    const int S = sy * 65536 + sx;
+    const uint32_t a0 = s_base + 4u * (uint32_t)((y - cy0 - 32) * AP + (x - cx0 - 32));
+    uint32_t bias = 0x80008000u;
+    asm volatile("" : "+r"(bias));          // opaque: keeps the bias inside the running value instead of one add per vote
+    uint32_t U = bias + (uint32_t)t_lo * (uint32_t)S;
+    int t = t_lo;
+    for (; t + 7 <= t_hi; t += 8, U += 8u * (uint32_t)S) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) vote_at(a0, U + (uint32_t)k * (uint32_t)S);
+    }
+    for (; t <= t_hi; t++, U += (uint32_t)S) vote_at(a0, U);
     if (t_lo <= 0 && t_hi >= 0) atomicAdd(s_acc + (y - cy0) * AP + (x - cx0), -1);
 }
 
-template <int UNROLL>
-__global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks2(const uint2 *__restrict__ edges,
-                                                              const int2 *__restrict__ dir, int nbx, int nby, int h,
-                                                              int w, int32_t *cand, int32_t *ncand, int cand_cap)
+__global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks(const uint2 *__restrict__ edges, size_t estride,
+                                                             const int2 *__restrict__ dir, int nbx, int nby, const Dims dims,
+                                                             int n_images, int32_t *cand, int32_t *ncand, int cand_cap)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     int *s_acc = reinterpret_cast<int *>(s_raw);                       // AS x AP
     __shared__ int s_boff[VB * VB], s_bend[VB * VB + 1];               // bucket slice start / running item end
     constexpr int NW = VOTE_THREADS / 32;
-    const size_t plane = (size_t)h * w;
     const int map = blockIdx.z;
-    const uint2 *elist = edges + map * plane;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int2 wh = dims.of(map % n_images);
+    const int w = wh.x, h = wh.y;
     const int tx0 = blockIdx.x * AT, ty0 = blockIdx.y * AT;
+    if (tx0 >= w || ty0 >= h) return;                                  // tile outside this image (ragged batch)
+    const uint2 *elist = edges + map * estride;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cx0 = tx0 - 1 - AG, cy0 = ty0 - 1 - AG;
     const int X0 = max(tx0 - 1, 0), X1 = min(tx0 + AT, w - 1);
     const int Y0 = max(ty0 - 1, 0), Y1 = min(ty0 + AT, h - 1);
@@ -383,6 +221,7 @@ __global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks2(const uint2 *__res
     __syncthreads();
     const int items = s_bend[nb];
     {
+        const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_acc);
         const int per = ((items + NW - 1) / NW + 31) & ~31;          // items per warp, whole rounds of 32
         const int i0 = warp * per, i1 = min(i0 + per, items);
         int b = 0;
@@ -399,7 +238,7 @@ __global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks2(const uint2 *__res
             const uint2 e = __ldg(elist + s_boff[b] + (it - s_bend[b]));
             const int x = e.x & 0xffff, y = e.x >> 16;
             if (e.y == 0 || x < rx0 || x > rx1 || y < ry0 || y > ry1) continue;
-            vote_item<UNROLL>(s_acc, e, cx0, cy0, X0, X1, Y0, Y1);
+            vote_item(s_acc, s_base, e, cx0, cy0, X0, X1, Y0, Y1);
         }
     }
     __syncthreads();
@@ -436,7 +275,7 @@ __global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks2(const uint2 *__res
 
 // ------------------------------------------------------------------ K7a: radius estimation
 // One warp per candidate centre.  Only pixels within 30 px can contribute, so the warp scans
-// the 60x60 window of the edge map around the centre instead of the whole non-zero list.
+// the edge-list buckets around the centre instead of the whole non-zero list.
 __device__ __forceinline__ float radius_of_q(int q)
 {
     // (upbin + j)/2.f / nBinsPerDr * dr + minRadius, every step rounded to float32
@@ -447,11 +286,11 @@ constexpr int RW = 8;          // warps per block
 constexpr int RBINS = 320;     // NBINS padded to a multiple of 32 (pad stays zero)
 constexpr int RQ = 576;        // radius table size: q = upbin + j <= 289 + 279
 
-__global__ void __launch_bounds__(RW * 32) k_radius(const uint2 *__restrict__ edges, const int2 *__restrict__ dir,
-                                                   int nbx, int nby, int h, int w,
-                                                   const int32_t *__restrict__ cand, const int32_t *__restrict__ ncand,
-                                                   int cand_cap, unsigned long long *est, int32_t *nest, int32_t *status,
-                                                   int n_images)
+__global__ void __launch_bounds__(RW * 32) k_radius(const uint2 *__restrict__ edges, size_t estride,
+                                                   const int2 *__restrict__ dir, int nbx, int nby, const Dims dims,
+                                                   int n_images, const int32_t *__restrict__ cand,
+                                                   const int32_t *__restrict__ ncand, int cand_cap, unsigned long long *est,
+                                                   int32_t *nest, int32_t *status)
 {
     __shared__ int s_bins[RW][RBINS];
     __shared__ int s_pref[RW][RBINS];
@@ -460,15 +299,17 @@ __global__ void __launch_bounds__(RW * 32) k_radius(const uint2 *__restrict__ ed
     __shared__ uint16_t s_binlut[900];             // histogram bin of squared distance q + 0.5, q = 1..899
     const int map = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint2 *elist = edges + (size_t)map * h * w;
-    const int2 *mdir = dir + (size_t)map * nbx * nby;
-    const int aw = w + 2;
     int n = ncand[map];
     if (n > cand_cap) {
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(status + map % n_images, I2S_ST_CAND_OVERFLOW);
         n = cand_cap;
     }
     if (blockIdx.x * RW >= n) return;
+    const int2 wh = dims.of(map % n_images);
+    const int w = wh.x, h = wh.y;
+    const uint2 *elist = edges + map * estride;
+    const int2 *mdir = dir + (size_t)map * nbx * nby;
+    const int aw = w + 2;
     for (int q = threadIdx.x; q < RQ; q += blockDim.x) s_rtab[q] = radius_of_q(q);
     // Centres sit on half-integers and edge pixels on integers, so the float32 squared distance
     // (cx+.5-px)^2 + (cy+.5-py)^2 is exactly q + 0.5 with q = dx(dx+1) + dy(dy+1) an integer: the
@@ -567,63 +408,127 @@ __global__ void __launch_bounds__(RW * 32) k_radius(const uint2 *__restrict__ ed
 }
 
 // ------------------------------------------------------------------ K7b: total-order sort + greedy minDist
-// One block per map: bitonic sort of the packed keys (support desc, radius desc, x asc, y asc),
-// then warp 0 runs the sequential suppression (kept iff >= 10 px from every kept circle).  Kept
-// circles are hashed into a grid of cells at least 16 px wide, so a candidate only has to be
-// compared with the chains of its 3x3 cell neighbourhood (lanes 0..8, one cell each).
+// One block per map: bitonic sort of the packed keys (support desc, radius desc, x asc, y asc), then
+// OpenCV's sequential suppression -- a circle is kept iff it is >= 10 px from every circle kept
+// before it -- evaluated in parallel.  All candidates are hashed into a grid of cells at least 16 px
+// wide; every round each undecided candidate looks at the EARLIER candidates within 10 px (chains of
+// its 3x3 cell neighbourhood): one of them kept => rejected; all of them rejected => kept; otherwise
+// it waits.  The earliest undecided candidate is always decided, so the loop ends, and every decision
+// is the sequential algorithm's by induction over the sorted order -- a handful of rounds instead of
+// one dependent step per candidate.  The kept circles are compacted in sorted order by a block scan.
+//
+// Working arrays (15 bytes per candidate) live in shared memory up to 8192 candidates per map and in
+// the caller's workspace above that, so any cand_cap the limits accept runs.
+struct FinishBufs {
+    unsigned long long *keys;        // np2cap
+    short2 *xy;                      // np2cap
+    uint16_t *next;                  // np2cap
+    uint8_t *state;                  // np2cap   0 undecided, 1 kept, 2 rejected
+};
+constexpr int FINISH_SMEM_CAP = 8192;
+constexpr int FINISH_MAX_CELLS = 4096;
+__host__ __device__ static inline size_t finish_bytes_per_map(int np2cap) { return (size_t)np2cap * 16; }
+
 __global__ void __launch_bounds__(256) k_circles_finish(const unsigned long long *__restrict__ est,
                                                         const int32_t *__restrict__ nest, int cand_cap, int np2cap,
                                                         int cshift, int cells_x, int cells_y, float *circ,
-                                                        int32_t *ncirc, int circle_cap, int32_t *status, int n_images)
+                                                        int32_t *ncirc, int circle_cap, int32_t *status, int n_images,
+                                                        unsigned char *gbuf)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    unsigned long long *keys = reinterpret_cast<unsigned long long *>(s_raw);          // np2cap
-    short2 *kept = reinterpret_cast<short2 *>(keys + np2cap);                          // np2cap
-    uint16_t *next = reinterpret_cast<uint16_t *>(kept + np2cap);                      // np2cap
-    uint16_t *head = next + np2cap;                                                    // cells_x * cells_y
+    __shared__ int s_flag, s_warp_tot[8];
     const int map = blockIdx.x;
-    int n = min(nest[map], cand_cap);
+    int *head = reinterpret_cast<int *>(s_raw);                                            // cells_x * cells_y
+    unsigned char *arr = gbuf ? gbuf + (size_t)map * finish_bytes_per_map(np2cap)
+                              : s_raw + (((size_t)cells_x * cells_y * 4 + 15) & ~(size_t)15);
+    FinishBufs B;
+    B.keys = reinterpret_cast<unsigned long long *>(arr);
+    B.xy = reinterpret_cast<short2 *>(B.keys + np2cap);
+    B.next = reinterpret_cast<uint16_t *>(B.xy + np2cap);
+    B.state = reinterpret_cast<uint8_t *>(B.next + np2cap);
+    const int n = min(nest[map], cand_cap);
     int np2 = 1;
     while (np2 < n) np2 <<= 1;
-    for (int i = threadIdx.x; i < np2; i += blockDim.x)
-        keys[i] = i < n ? est[(size_t)map * cand_cap + i] : ~0ull;
-    for (int i = threadIdx.x; i < cells_x * cells_y; i += blockDim.x) head[i] = 0xffff;
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) B.keys[i] = i < n ? est[(size_t)map * cand_cap + i] : ~0ull;
+    for (int i = threadIdx.x; i < cells_x * cells_y; i += blockDim.x) head[i] = -1;
     __syncthreads();
-    bitonic_sort_block(keys, np2);
-    if (threadIdx.x >= 32) return;
-    const int lane = threadIdx.x;
-    const int ddx = lane % 3 - 1, ddy = lane / 3 - 1;      // lanes 0..8: the 3x3 cell neighbourhood
-    int nk = 0;
-    float *out = circ + (size_t)map * circle_cap * 3;
-    for (int i = 0; i < n; i++) {
-        unsigned long long k = keys[i];
-        int x = (int)((k >> 14) & 0x3fff), y = (int)(k & 0x3fff);
-        const int cx = x >> cshift, cy = y >> cshift;
-        bool clash = false;
-        if (lane < 9) {
-            int ncx = cx + ddx, ncy = cy + ddy;
-            if (ncx >= 0 && ncx < cells_x && ncy >= 0 && ncy < cells_y) {
-                for (int j = head[ncy * cells_x + ncx]; j != 0xffff; j = next[j]) {
-                    int dx = kept[j].x - x, dy = kept[j].y - y;
-                    clash |= dx * dx + dy * dy < 100;
+    bitonic_sort_block(B.keys, np2);
+    // hash every candidate into its cell (chain order is irrelevant: the index decides priority)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long k = B.keys[i];
+        const int x = (int)((k >> 14) & 0x3fff), y = (int)(k & 0x3fff);
+        B.xy[i] = make_short2((short)x, (short)y);
+        B.state[i] = 0;
+        const int prev = atomicExch(&head[(y >> cshift) * cells_x + (x >> cshift)], i);
+        B.next[i] = (uint16_t)(prev < 0 ? 0xffff : prev);
+    }
+    volatile uint8_t *vstate = B.state;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_flag = 0;
+        __syncthreads();
+        bool waiting = false;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            if (vstate[i]) continue;
+            const short2 p = B.xy[i];
+            const int ccx = p.x >> cshift, ccy = p.y >> cshift;
+            bool any_kept = false, all_rejected = true;
+            for (int dy = -1; dy <= 1; dy++) {
+                const int ny = ccy + dy;
+                if (ny < 0 || ny >= cells_y) continue;
+                for (int dx = -1; dx <= 1; dx++) {
+                    const int nx = ccx + dx;
+                    if (nx < 0 || nx >= cells_x) continue;
+                    for (int j = head[ny * cells_x + nx]; j >= 0; j = (B.next[j] == 0xffff) ? -1 : (int)B.next[j]) {
+                        if (j >= i) continue;
+                        const short2 q = B.xy[j];
+                        const int ex = q.x - p.x, ey = q.y - p.y;
+                        if (ex * ex + ey * ey >= 100) continue;
+                        const int s = vstate[j];
+                        any_kept |= s == 1;
+                        all_rejected &= s == 2;
+                    }
                 }
             }
+            if (any_kept) vstate[i] = 2;
+            else if (all_rejected) vstate[i] = 1;
+            else waiting = true;
         }
-        if (__any_sync(0xffffffffu, clash)) continue;
-        if (lane == 0) {
-            kept[nk] = make_short2((short)x, (short)y);
-            next[nk] = head[cy * cells_x + cx];
-            head[cy * cells_x + cx] = (uint16_t)nk;
-            if (nk < circle_cap) {
-                out[3 * nk] = (float)x + 0.5f;
-                out[3 * nk + 1] = (float)y + 0.5f;
-                out[3 * nk + 2] = radius_of_q(1023 - (int)((k >> 28) & 0x3ff));
-            }
-        }
-        nk++;
-        __syncwarp();
+        if (waiting) s_flag = 1;
+        __syncthreads();
+        if (!s_flag) break;
     }
-    if (lane == 0) {
+    // kept circles in sorted order: contiguous slice per thread, block scan of the kept counts
+    const int per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int i0 = min((int)threadIdx.x * per, n), i1 = min(i0 + per, n);
+    int mine = 0;
+    for (int i = i0; i < i1; i++) mine += B.state[i] == 1;
+    int incl = mine;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp_tot[warp] = incl;
+    __syncthreads();
+    int before = incl - mine, nk = 0;
+    for (int k = 0; k < 8; k++) {
+        if (k < warp) before += s_warp_tot[k];
+        nk += s_warp_tot[k];
+    }
+    float *out = circ + (size_t)map * circle_cap * 3;
+    for (int i = i0; i < i1; i++) {
+        if (B.state[i] != 1) continue;
+        if (before < circle_cap) {
+            const unsigned long long k = B.keys[i];
+            out[3 * before] = (float)B.xy[i].x + 0.5f;
+            out[3 * before + 1] = (float)B.xy[i].y + 0.5f;
+            out[3 * before + 2] = radius_of_q(1023 - (int)((k >> 28) & 0x3ff));
+        }
+        before++;
+    }
+    if (threadIdx.x == 0) {
         ncirc[map] = nk;
         if (nk > circle_cap) atomicOr(status + map % n_images, I2S_ST_CIRCLE_OVERFLOW);
     }
@@ -672,8 +577,8 @@ __device__ __forceinline__ void circle_rect(const float *c, int &x0, int &y0, in
     x1 = __float2int_rn(__fadd_rn(c[0], r)); y1 = __float2int_rn(__fadd_rn(c[1], r));
 }
 
-__global__ void __launch_bounds__(256) k_mask(const uint8_t *__restrict__ edges, uint8_t *__restrict__ masked, int h,
-                                              int w, const float *__restrict__ circles,
+__global__ void __launch_bounds__(256) k_mask(const uint8_t *__restrict__ edges, uint8_t *__restrict__ masked,
+                                              const Dims dims, int pitch, size_t stride, const float *__restrict__ circles,
                                               const int32_t *__restrict__ counts, int circle_cap,
                                               const int2 *__restrict__ dup)
 {
@@ -681,13 +586,15 @@ __global__ void __launch_bounds__(256) k_mask(const uint8_t *__restrict__ edges,
     __shared__ int s_idx[KCHUNK];
     __shared__ int s_n;
     const int img = blockIdx.z;
-    const size_t plane = (size_t)h * w;
+    const int2 wh = dims.of(img);
+    const int w = wh.x, h = wh.y;
+    const int tx0 = blockIdx.x * KT, ty0 = blockIdx.y * KT;
+    if (tx0 >= w || ty0 >= h) return;                              // tile outside this image (ragged batch)
     const float *circ = circles + (size_t)img * circle_cap * 3;
     const int n = min(counts[img], circle_cap);
     // circles [0, n0) and [n0 + n1, 2 n0 + n1) are repeated verbatim at [2 n0 + n1, 3 n0 + n1) (see k_stack)
     const int2 dd = dup ? dup[img] : make_int2(0, 0);
     const int skip_a = dd.x, skip_b0 = dd.x + dd.y, skip_b1 = 2 * dd.x + dd.y;
-    const int tx0 = blockIdx.x * KT, ty0 = blockIdx.y * KT;
     const int tx1 = min(tx0 + KT, w) - 1, ty1 = min(ty0 + KT, h) - 1;
     int last[16];
 #pragma unroll
@@ -726,31 +633,46 @@ __global__ void __launch_bounds__(256) k_mask(const uint8_t *__restrict__ edges,
             }
         }
     }
+    const bool al = ((reinterpret_cast<uintptr_t>(edges) | reinterpret_cast<uintptr_t>(masked) | (uintptr_t)pitch | (uintptr_t)stride) & 3) == 0;
+    const int wlim = write_limit(w, pitch, 4);
+    const int x = tx0 + lx;
+    if (x >= w) return;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         int y = ty0 + ly + 16 * q;
         if (y >= h) continue;
+        const size_t o = img * stride + (size_t)y * pitch;
+        uint32_t src = 0;
+        if (al && x + 3 < wlim) src = *reinterpret_cast<const uint32_t *>(edges + o + x);
+        else
+            for (int k = 0; k < 4 && x + k < w; k++) src |= (uint32_t)edges[o + x + k] << (8 * k);
+        uint32_t res = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            int x = tx0 + lx + k;
-            if (x >= w) continue;
-            size_t o = img * plane + (size_t)y * w + x;
-            int li = last[q * 4 + k];
-            uint8_t v;
-            if (li < 0) v = edges[o];
+            const int li = last[q * 4 + k];
+            uint32_t v;
+            if (li < 0) v = (src >> (8 * k)) & 0xffu;
             else {
                 int mx = __float2int_rn(circ[3 * li]), my = __float2int_rn(circ[3 * li + 1]);
-                v = (abs(x - mx) + abs(y - my) <= 1) ? 255 : 0;
+                v = (abs(x + k - mx) + abs(y - my) <= 1) ? 255u : 0u;
             }
-            masked[o] = v;
+            res |= v << (8 * k);
         }
+        store4(masked + o, x, w, wlim, al, res);
     }
 }
 
 // ------------------------------------------------------------------ host orchestration
+static int p2_of(int v)
+{
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
 size_t circles_scratch_bytes(int maps, int h, int w, const i2s_limits_t &lim)
 {
-    size_t plane = (size_t)h * w;
+    const size_t plane = (size_t)h * canvas_pitch(w);
     size_t b = 0;
     b += align_up(maps * plane, 256);                               // state maps
     b += align_up(maps * plane * 8, 256);                           // edge lists (position, Q10 step), worst case
@@ -758,17 +680,19 @@ size_t circles_scratch_bytes(int maps, int h, int w, const i2s_limits_t &lim)
     b += align_up((size_t)maps * lim.cand_cap * 4, 256);            // candidate centres
     b += align_up((size_t)maps * lim.cand_cap * 8, 256);            // estimated circle keys
     b += align_up((size_t)maps * 4 * 4, 256);                       // counters
-    b += align_up((size_t)maps * lim.circle_cap * 12, 256);         // per-map circles
+    if (lim.cand_cap > FINISH_SMEM_CAP) b += align_up((size_t)maps * finish_bytes_per_map(p2_of(lim.cand_cap)), 256);
     b += canny_scratch_bytes(maps, h, w);
     return b + 4096;
 }
 
 // HoughCircles on every map of `ms`; per-map circles [maps][circle_cap][3] + counts [maps]
-int hough_circles_maps(const MapSet &ms, int h, int w, float *mcirc, int32_t *mcount, int32_t *status,
+int hough_circles_maps(const MapSet &ms, const Dims &dims, float *mcirc, int32_t *mcount, int32_t *status,
                        const i2s_limits_t &lim, Arena &ar, cudaStream_t st)
 {
     const int maps = ms.count * ms.n;
-    const size_t plane = (size_t)h * w;
+    const int h = dims.h, w = dims.w;
+    const int spitch = canvas_pitch(w);
+    const size_t plane = (size_t)h * spitch;
     uint8_t *state = ar.take<uint8_t>(maps * plane);
     uint2 *edges = ar.take<uint2>(maps * plane);
     const int nbx = cdiv(w, EB), nby = cdiv(h, EB);
@@ -776,65 +700,64 @@ int hough_circles_maps(const MapSet &ms, int h, int w, float *mcirc, int32_t *mc
     int32_t *cand = ar.take<int32_t>((size_t)maps * lim.cand_cap);
     unsigned long long *est = ar.take<unsigned long long>((size_t)maps * lim.cand_cap);
     int32_t *ctr = ar.take<int32_t>((size_t)maps * 3);
+    const int np2 = p2_of(lim.cand_cap);
+    unsigned char *gbuf = lim.cand_cap > FINISH_SMEM_CAP ? ar.take<unsigned char>((size_t)maps * finish_bytes_per_map(np2)) : nullptr;
     void *cscratch = ar.take<uint8_t>(canny_scratch_bytes(maps, h, w));
     if (!ar.ok()) { set_error("hough_circles: workspace too small"); return I2S_E_WORKSPACE; }
+    I2S_ARG(maps < 65536 && nby < 65536);
     int32_t *ncand = ctr, *nest = ctr + maps, *ecount = ctr + 2 * maps;
 
-    int rc = canny_states(ms, 1, state, h, w, CANNY_LOW, CANNY_HIGH, lim.hyst_passes, status, cscratch, st);
+    int rc = canny_states(ms, dims, 1, state, spitch, plane, CANNY_LOW, CANNY_HIGH, lim.hyst_passes, status, cscratch, st,
+                          nullptr, 0, 0);
     if (rc) return rc;
     I2S_CUDA(cudaMemsetAsync(ctr, 0, sizeof(int32_t) * maps * 3, st));
-    bool al = (w & 3) == 0 && ((uintptr_t)state & 3) == 0;
-    const bool fine = (w & 15) == 0 && ((uintptr_t)state & 15) == 0 && !legacy_enabled("edges");   // list has 16x16 sub-buckets
     {
         ScopedSection sec(SEC_EDGE_LIST, st);
-        const dim3 eg(cdiv(nbx, 2), cdiv(nby, 2), maps);
-        if (fine)
-            k_edge_buckets16<<<eg, 256, 0, st>>>(ms, state, h, w, edges, ecount, dir, nbx, nby);
-        else
-            k_edge_buckets<<<eg, 256, 0, st>>>(ms, state, h, w, al, edges, ecount, dir, nbx, nby);
-        I2S_CHECK_LAUNCH("k_edge_buckets");
+        k_edge_list<<<dim3(cdiv(nbx, EL_WARPS), nby, maps), EL_WARPS * 32, 0, st>>>(ms, dims, state, spitch, plane, edges, plane,
+                                                                                   ecount, dir, nbx, nby);
+        I2S_CHECK_LAUNCH("k_edge_list");
     }
     {
         ScopedSection sec(SEC_VOTE, st);
-        auto kern = legacy_enabled("vote") ? k_vote_peaks : legacy_enabled("vote4") ? k_vote_peaks2<4> : k_vote_peaks2<8>;
-        I2S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, VOTE_SMEM));
-        kern<<<dim3(cdiv(w, AT), cdiv(h, AT), maps), VOTE_THREADS, VOTE_SMEM, st>>>(edges, dir, nbx, nby, h, w, cand, ncand,
-                                                                                   lim.cand_cap);
+        I2S_CUDA(cudaFuncSetAttribute(k_vote_peaks, cudaFuncAttributeMaxDynamicSharedMemorySize, VOTE_SMEM));
+        k_vote_peaks<<<dim3(cdiv(w, AT), cdiv(h, AT), maps), VOTE_THREADS, VOTE_SMEM, st>>>(edges, plane, dir, nbx, nby, dims, ms.n,
+                                                                                           cand, ncand, lim.cand_cap);
         I2S_CHECK_LAUNCH("k_vote_peaks");
     }
     {
         ScopedSection sec(SEC_RADIUS, st);
         // (a variant with four centres per warp -- 8 lanes each, 16-bit bins -- cut the instruction count by
         // 18 % but not the time: the loop over the bucket entries dominates, not the per-centre scan)
-        k_radius<<<dim3(16, maps), RW * 32, 0, st>>>(edges, dir, nbx, nby, h, w, cand, ncand, lim.cand_cap, est, nest, status, ms.n);
+        k_radius<<<dim3(16, maps), RW * 32, 0, st>>>(edges, plane, dir, nbx, nby, dims, ms.n, cand, ncand, lim.cand_cap, est, nest,
+                                                     status);
         I2S_CHECK_LAUNCH("k_radius");
     }
     ScopedSection sec(SEC_CIRCLES_FINISH, st);
-    int np2 = 1;
-    while (np2 < lim.cand_cap) np2 <<= 1;
-    int cshift = 4;                                            // cells of >= 16 px (> minDist), at most 16384 of them
-    while ((size_t)((w >> cshift) + 1) * ((h >> cshift) + 1) > 16384) cshift++;
+    int cshift = 4;                                            // cells of >= 16 px (> minDist)
+    while ((size_t)((w >> cshift) + 1) * ((h >> cshift) + 1) > FINISH_MAX_CELLS) cshift++;
     const int cells_x = (w >> cshift) + 1, cells_y = (h >> cshift) + 1;
-    size_t smem = (size_t)np2 * (8 + 4 + 2) + (size_t)cells_x * cells_y * 2;
+    size_t smem = (((size_t)cells_x * cells_y * 4 + 15) & ~(size_t)15) + (gbuf ? 0 : finish_bytes_per_map(np2));
     I2S_CUDA(cudaFuncSetAttribute(k_circles_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_circles_finish<<<maps, 256, smem, st>>>(est, nest, lim.cand_cap, np2, cshift, cells_x, cells_y, mcirc, mcount,
-                                              lim.circle_cap, status, ms.n);
+                                              lim.circle_cap, status, ms.n, gbuf);
     I2S_CHECK_LAUNCH("k_circles_finish");
     return I2S_OK;
 }
 
-int mask_circles(const uint8_t *edges, uint8_t *masked, int n, int h, int w, const float *circles,
-                 const int32_t *counts, int circle_cap, cudaStream_t st, const int2 *dup)
+int mask_circles(const uint8_t *edges, uint8_t *masked, const Dims &dims, int n, int pitch, size_t stride,
+                 const float *circles, const int32_t *counts, int circle_cap, cudaStream_t st, const int2 *dup)
 {
     ScopedSection sec(SEC_MASK, st);
-    k_mask<<<dim3(cdiv(w, KT), cdiv(h, KT), n), 256, 0, st>>>(edges, masked, h, w, circles, counts, circle_cap, dup);
+    I2S_ARG(n < 65536);
+    k_mask<<<dim3(cdiv(dims.w, KT), cdiv(dims.h, KT), n), 256, 0, st>>>(edges, masked, dims, pitch, stride, circles, counts,
+                                                                       circle_cap, dup);
     I2S_CHECK_LAUNCH("k_mask");
     return I2S_OK;
 }
 
 size_t find_circles_scratch_bytes(int n, int h, int w, const i2s_limits_t &lim)
 {
-    size_t plane = (size_t)h * w;
+    const size_t plane = (size_t)h * canvas_pitch(w);
     size_t b = 6 * align_up((size_t)n * plane, 256);                       // the six blurred copies
     b += align_up((size_t)n * I2S_N_UNIQUE * lim.circle_cap * 12, 256);    // per-map circles
     b += align_up((size_t)n * I2S_N_UNIQUE * 4, 256);
@@ -842,12 +765,16 @@ size_t find_circles_scratch_bytes(int n, int h, int w, const i2s_limits_t &lim)
     return b + circles_scratch_bytes(n * I2S_N_UNIQUE, h, w, lim) + 4096;
 }
 
-int find_circles(const uint8_t *grey, const uint8_t *edges, int n, int h, int w, float *circles, int32_t *counts,
-                 uint8_t *masked, int32_t *status, const i2s_limits_t &lim, Arena &ar, cudaStream_t st)
+// grey / edges: [n] planes of `pitch` bytes per row, dims.h rows apart (the caller's planes); the blurred
+// copies live in the workspace on the library's own canvas pitch
+int find_circles(const uint8_t *grey, const uint8_t *edges, const Dims &dims, int n, int pitch, float *circles,
+                 int32_t *counts, uint8_t *masked, int32_t *status, const i2s_limits_t &lim, Arena &ar, cudaStream_t st)
 {
-    const size_t plane = (size_t)h * w;
+    const int h = dims.h, w = dims.w;
+    const int bpitch = canvas_pitch(w);
+    const size_t bplane = (size_t)h * bpitch;
     uint8_t *blur[6];
-    for (int k = 0; k < 6; k++) blur[k] = ar.take<uint8_t>((size_t)n * plane);
+    for (int k = 0; k < 6; k++) blur[k] = ar.take<uint8_t>((size_t)n * bplane);
     const int maps = n * I2S_N_UNIQUE;
     float *mcirc = ar.take<float>((size_t)maps * lim.circle_cap * 3);
     int32_t *mcount = ar.take<int32_t>(maps);
@@ -855,31 +782,33 @@ int find_circles(const uint8_t *grey, const uint8_t *edges, int n, int h, int w,
     if (!ar.ok()) { set_error("find_circles: workspace too small"); return I2S_E_WORKSPACE; }
     // internal order: grey, edges, med3, gau3, med5, gau5, med7, gau7
     int rc;
-    if ((rc = i2s_gauss357(grey, blur[1], blur[3], blur[5], n, h, w, st))) return rc;
-    if ((rc = median357(grey, blur[0], blur[2], blur[4], n, h, w, st))) return rc;
+    const size_t gstride = (size_t)h * pitch;
+    if ((rc = gauss357(grey, pitch, gstride, blur[1], blur[3], blur[5], bpitch, bplane, dims, n, st))) return rc;
+    if ((rc = median357(grey, pitch, gstride, blur[0], blur[2], blur[4], bpitch, bplane, dims, n, st))) return rc;
     MapSet ms{};
-    ms.src[0] = grey; ms.src[1] = edges;
-    for (int k = 0; k < 6; k++) ms.src[2 + k] = blur[k];
-    ms.count = I2S_N_UNIQUE; ms.n = n;
-    if ((rc = hough_circles_maps(ms, h, w, mcirc, mcount, status, lim, ar, st))) return rc;
+    ms.n = n;
+    ms.add(grey, pitch, h);
+    ms.add(edges, pitch, h);
+    for (int k = 0; k < 6; k++) ms.add(blur[k], bpitch, h);
+    if ((rc = hough_circles_maps(ms, dims, mcirc, mcount, status, lim, ar, st))) return rc;
     {
         ScopedSection sec(SEC_STACK, st);
         k_stack<<<n, 256, 0, st>>>(mcirc, mcount, n, lim.circle_cap, circles, counts, status, dup);
         I2S_CHECK_LAUNCH("k_stack");
     }
-    return mask_circles(edges, masked, n, h, w, circles, counts, lim.circle_cap, st, legacy_enabled("mask") ? nullptr : dup);
+    return mask_circles(edges, masked, dims, n, pitch, (size_t)h * pitch, circles, counts, lim.circle_cap, st, dup);
 }
 
-}  // namespace i2s
-
-using namespace i2s;
-
-static int check_limits(const i2s_limits_t *lim)
+int check_limits(const i2s_limits_t *lim)
 {
     I2S_ARG(lim && lim->cand_cap >= 32 && lim->cand_cap <= 16384 && lim->circle_cap >= 1 && lim->line_cap >= 2 &&
             lim->line_cap <= 4096 && lim->hyst_passes >= 1);
     return I2S_OK;
 }
+
+}  // namespace i2s
+
+using namespace i2s;
 
 extern "C" size_t i2s_hough_circles_workspace_bytes(int n, int h, int w, const i2s_limits_t *lim)
 {
@@ -887,24 +816,29 @@ extern "C" size_t i2s_hough_circles_workspace_bytes(int n, int h, int w, const i
     return circles_scratch_bytes(n, h, w, *lim);
 }
 
-extern "C" int i2s_hough_circles(const uint8_t *img, int n, int h, int w, float *circles, int32_t *counts,
+extern "C" int i2s_hough_circles(const uint8_t *img, int pitch, int n, int h, int w, float *circles, int32_t *counts,
                                  int32_t *status, const i2s_limits_t *lim, void *ws, size_t ws_bytes, void *stream)
 {
     I2S_ARG(img && circles && counts && status && ws && n >= 0 && h > 0 && w > 0 && h < 16384 && w < 16384);
+    if (pitch == 0) pitch = w;
+    I2S_ARG(pitch >= w);
     int rc = check_limits(lim);
     if (rc) return rc;
     if (n == 0) return I2S_OK;
     Arena ar(ws, ws_bytes);
-    MapSet ms = MapSet::single(img, n);
-    return hough_circles_maps(ms, h, w, circles, counts, status, *lim, ar, (cudaStream_t)stream);
+    MapSet ms = MapSet::single(img, pitch, h, n);
+    return hough_circles_maps(ms, Dims::uniform(h, w), circles, counts, status, *lim, ar, (cudaStream_t)stream);
 }
 
-extern "C" int i2s_mask_circles(const uint8_t *edges, uint8_t *masked, int n, int h, int w, const float *circles,
+extern "C" int i2s_mask_circles(const uint8_t *edges, uint8_t *masked, int pitch, int n, int h, int w, const float *circles,
                                 const int32_t *counts, int circle_cap, void *stream)
 {
     I2S_ARG(edges && masked && circles && counts && n >= 0 && h > 0 && w > 0 && circle_cap > 0);
+    if (pitch == 0) pitch = w;
+    I2S_ARG(pitch >= w);
     if (n == 0) return I2S_OK;
-    return mask_circles(edges, masked, n, h, w, circles, counts, circle_cap, (cudaStream_t)stream, nullptr);
+    return mask_circles(edges, masked, Dims::uniform(h, w), n, pitch, (size_t)h * pitch, circles, counts, circle_cap,
+                        (cudaStream_t)stream, nullptr);
 }
 
 extern "C" size_t i2s_find_circles_workspace_bytes(int n, int h, int w, const i2s_limits_t *lim)
@@ -913,15 +847,18 @@ extern "C" size_t i2s_find_circles_workspace_bytes(int n, int h, int w, const i2
     return find_circles_scratch_bytes(n, h, w, *lim);
 }
 
-extern "C" int i2s_find_circles(const uint8_t *grey, const uint8_t *edges, int n, int h, int w, float *circles,
+extern "C" int i2s_find_circles(const uint8_t *grey, const uint8_t *edges, int pitch, int n, int h, int w, float *circles,
                                 int32_t *counts, uint8_t *masked, int32_t *status, const i2s_limits_t *lim, void *ws,
                                 size_t ws_bytes, void *stream)
 {
     I2S_ARG(grey && edges && circles && counts && masked && status && ws && n >= 0 && h > 0 && w > 0 && h < 16384 &&
             w < 16384);
+    if (pitch == 0) pitch = w;
+    I2S_ARG(pitch >= w);
     int rc = check_limits(lim);
     if (rc) return rc;
     if (n == 0) return I2S_OK;
     Arena ar(ws, ws_bytes);
-    return find_circles(grey, edges, n, h, w, circles, counts, masked, status, *lim, ar, (cudaStream_t)stream);
+    return find_circles(grey, edges, Dims::uniform(h, w), n, pitch, circles, counts, masked, status, *lim, ar,
+                        (cudaStream_t)stream);
 }

@@ -45,17 +45,21 @@ __device__ __forceinline__ int rho_of(const Trig &t, int a, int j, int i)
 // and are flushed with one global atomic per touched bin.
 constexpr int LT_W = 256, LT_H = 32, LBINS = 320;
 
-__global__ void __launch_bounds__(256) k_line_vote(const uint8_t *__restrict__ masked, int32_t *__restrict__ acc, int h,
-                                                   int w, const Trig trig, bool al)
+__global__ void __launch_bounds__(256) k_line_vote(const uint8_t *__restrict__ masked, int pitch, size_t stride,
+                                                   int32_t *__restrict__ acc, size_t acc_stride, const Dims dims,
+                                                   const Trig trig)
 {
     __shared__ int s_acc[NANG][LBINS];
     __shared__ int s_base[NANG];
     const int img = blockIdx.z;
-    const size_t plane = (size_t)h * w;
-    const uint8_t *src = masked + img * plane;
-    const int numrho = 2 * (w + h) + 1, aw = numrho + 2, half = (numrho - 1) / 2;
-    int32_t *accm = acc + (size_t)img * ACC_ROWS * aw;
+    const int2 wh = dims.of(img);
+    const int w = wh.x, h = wh.y;
     const int x0 = blockIdx.x * LT_W, y0 = blockIdx.y * LT_H;
+    if (x0 >= w || y0 >= h) return;                               // tile outside this image (ragged batch)
+    const uint8_t *src = masked + img * stride;
+    const bool al = ((reinterpret_cast<uintptr_t>(masked) | (uintptr_t)pitch | (uintptr_t)stride) & 3) == 0;
+    const int numrho = 2 * (w + h) + 1, aw = numrho + 2, half = (numrho - 1) / 2;
+    int32_t *accm = acc + (size_t)img * acc_stride;
     const int x1 = min(x0 + LT_W, w) - 1, y1 = min(y0 + LT_H, h) - 1;
     for (int i = threadIdx.x; i < NANG * LBINS; i += blockDim.x) (&s_acc[0][0])[i] = 0;
     if (threadIdx.x < NANG) {
@@ -70,7 +74,7 @@ __global__ void __launch_bounds__(256) k_line_vote(const uint8_t *__restrict__ m
         int y = y0 + ty, x = x0 + gx;
         if (y >= h || x >= w) continue;
         uint32_t v = 0;
-        const uint8_t *p = src + (size_t)y * w + x;
+        const uint8_t *p = src + (size_t)y * pitch + x;
         if (al && x + 3 < w) v = __ldg(reinterpret_cast<const uint32_t *>(p));
         else
             for (int k = 0; k < 4 && x + k < w; k++) v |= (uint32_t)__ldg(p + k) << (8 * k);
@@ -132,15 +136,28 @@ __device__ void line_call(const int32_t *__restrict__ acc_call, int na, int numr
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) k_line_peaks(const int32_t *__restrict__ acc, int h, int w, int thr, float *rho,
-                                                    int32_t *counts, int line_cap, int cap_p2, int32_t *status)
+// threshold.get() of image i: its own value, else the batch's, else choose_threshold() (img2sgf.py:606-613)
+__device__ __forceinline__ int line_threshold_of(const Dims &dims, int i, int thr, int w, int h)
+{
+    if (dims.images && dims.images[i].line_threshold > 0) return dims.images[i].line_threshold;
+    if (thr > 0) return thr;
+    const int t = (int)((double)min(w, h) / 12.8 + 16.0);
+    return min(max(t, 20), 200);
+}
+
+__global__ void __launch_bounds__(256) k_line_peaks(const int32_t *__restrict__ acc, size_t acc_stride, const Dims dims,
+                                                    int thr_all, float *rho, int32_t *counts, int line_cap, int cap_p2,
+                                                    int32_t *status)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(s_raw);
     __shared__ int s_cnt;
     const int dir = blockIdx.x, img = blockIdx.y;
+    const int2 wh = dims.of(img);
+    const int w = wh.x, h = wh.y;
+    const int thr = line_threshold_of(dims, img, thr_all, w, h);
     const int numrho = 2 * (w + h) + 1, aw = numrho + 2;
-    const int32_t *accm = acc + (size_t)img * ACC_ROWS * aw;
+    const int32_t *accm = acc + (size_t)img * acc_stride;
     float *out = rho + ((size_t)img * 2 + dir) * line_cap;
     int out_n = 0;
     bool overflow = false;
@@ -206,25 +223,28 @@ static int p2_of(int v)
     return p;
 }
 
-int find_lines(const uint8_t *masked, int n, int h, int w, int threshold, float *rho, int32_t *counts, int line_cap,
-               int32_t *status, Arena &ar, cudaStream_t st)
+// masked: [n] planes of `pitch` bytes per row, `stride` bytes apart; threshold 0 = per-image value
+// (i2s_image_t.line_threshold, else choose_threshold())
+int find_lines(const uint8_t *masked, const Dims &dims, int n, int pitch, size_t stride, int threshold, float *rho,
+               int32_t *counts, int line_cap, int32_t *status, Arena &ar, cudaStream_t st)
 {
-    const size_t aw = 2 * (size_t)(w + h) + 3;
-    int32_t *acc = ar.take<int32_t>((size_t)n * ACC_ROWS * aw);
+    const int h = dims.h, w = dims.w;
+    const size_t acc_stride = ACC_ROWS * (2 * (size_t)(w + h) + 3);      // sized for the canvas; every image uses its own width
+    int32_t *acc = ar.take<int32_t>((size_t)n * acc_stride);
     if (!ar.ok()) { set_error("find_lines: workspace too small"); return I2S_E_WORKSPACE; }
-    I2S_CUDA(cudaMemsetAsync(acc, 0, (size_t)n * ACC_ROWS * aw * 4, st));
-    static const Trig trig = make_trig();
-    bool al = (w & 3) == 0 && ((uintptr_t)masked & 3) == 0;
+    I2S_ARG(n < 65536);
+    I2S_CUDA(cudaMemsetAsync(acc, 0, (size_t)n * acc_stride * 4, st));
+    const Trig trig = make_trig();
     {
         ScopedSection sec(SEC_LINE_VOTE, st);
-        k_line_vote<<<dim3(cdiv(w, LT_W), cdiv(h, LT_H), n), 256, 0, st>>>(masked, acc, h, w, trig, al);
+        k_line_vote<<<dim3(cdiv(w, LT_W), cdiv(h, LT_H), n), 256, 0, st>>>(masked, pitch, stride, acc, acc_stride, dims, trig);
         I2S_CHECK_LAUNCH("k_line_vote");
     }
     ScopedSection sec(SEC_LINE_PEAKS, st);
     int cap_p2 = p2_of(line_cap);
     size_t smem = (size_t)cap_p2 * 8;
     I2S_CUDA(cudaFuncSetAttribute(k_line_peaks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_line_peaks<<<dim3(2, n), 256, smem, st>>>(acc, h, w, threshold, rho, counts, line_cap, cap_p2, status);
+    k_line_peaks<<<dim3(2, n), 256, smem, st>>>(acc, acc_stride, dims, threshold, rho, counts, line_cap, cap_p2, status);
     I2S_CHECK_LAUNCH("k_line_peaks");
     return I2S_OK;
 }
@@ -249,13 +269,17 @@ extern "C" size_t i2s_find_lines_workspace_bytes(int n, int h, int w)
     return lines_scratch_bytes(n, h, w);
 }
 
-extern "C" int i2s_find_lines(const uint8_t *masked, int n, int h, int w, int threshold, float *rho, int32_t *counts,
-                              int line_cap, int32_t *status, void *ws, size_t ws_bytes, void *stream)
+extern "C" int i2s_find_lines(const uint8_t *masked, int pitch, int n, int h, int w, int threshold, float *rho,
+                              int32_t *counts, int line_cap, int32_t *status, void *ws, size_t ws_bytes, void *stream)
 {
-    I2S_ARG(masked && rho && counts && status && ws && n >= 0 && h > 0 && w > 0 && line_cap >= 2 && line_cap <= 4096);
+    I2S_ARG(masked && rho && counts && status && ws && n >= 0 && h > 0 && w > 0 && line_cap >= 2 && line_cap <= 4096 &&
+            threshold >= 0);
+    if (pitch == 0) pitch = w;
+    I2S_ARG(pitch >= w);
     if (n == 0) return I2S_OK;
     Arena ar(ws, ws_bytes);
-    return find_lines(masked, n, h, w, threshold, rho, counts, line_cap, status, ar, (cudaStream_t)stream);
+    return find_lines(masked, Dims::uniform(h, w), n, pitch, (size_t)h * pitch, threshold, rho, counts, line_cap, status, ar,
+                      (cudaStream_t)stream);
 }
 
 extern "C" int i2s_cluster(const float *rho, const int32_t *counts, int n, int line_cap, double *centres,

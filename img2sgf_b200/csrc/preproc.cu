@@ -1,10 +1,12 @@
-// preproc.cu -- greyscale, PIL contrast, fused Gaussian 3/5/7, median 3/5/7.
-// Reference call sites: img2sgf.py:142-144 (contrast), :153 (grey), :174 (median), :175 (Gaussian).
-// Arithmetic: SURVEY.md Appendix A.1, A.2, A.3, A.9 (all integer / fixed point, bit-exact).
+// preproc.cu -- greyscale, PIL contrast/brightness, fused Gaussian 3/5/7, median 3/5/7.
+// Reference call sites: img2sgf.py:142-149 (contrast, brightness), :153 (grey), :174 (median),
+// :175 (Gaussian).  Arithmetic: SURVEY.md Appendix A.1, A.2, A.3, A.9 (all integer / fixed point
+// or separately rounded float32, bit-exact).
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
+#include "preproc.cuh"
 #include "profile.cuh"
 #include "tma.cuh"
 #include "roll_cores.cuh"
@@ -20,15 +22,13 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 
-// I2S_LEGACY=name[,name...] selects the previous generation of a kernel (A/B runs on the GPU box).
-bool legacy_enabled(const char *name)
+int sm_count()
 {
-    const char *e = getenv("I2S_LEGACY");
-    if (!e) return false;
-    const size_t n = strlen(name);
-    for (const char *p = e; (p = strstr(p, name)) != nullptr; p += n)
-        if ((p == e || p[-1] == ',') && (p[n] == 0 || p[n] == ',')) return true;
-    return false;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        n <= 0)
+        return 148;
+    return n;
 }
 
 // ------------------------------------------------------------------ grey (A.1)
@@ -37,119 +37,116 @@ __device__ __forceinline__ uint32_t luma_q15(uint32_t c0, uint32_t c1, uint32_t 
     return (3735u * c0 + 19235u * c1 + 9798u * c2 + 16384u) >> 15;
 }
 
-// 4 pixels (12 bytes in, 4 bytes out) per thread; total = n*h*w pixels
-__global__ void __launch_bounds__(256) k_grey4(const uint32_t *__restrict__ rgb, uint32_t *__restrict__ grey,
-                                               size_t quads)
+// 4 pixels (12 bytes in, 4 bytes out) per thread; grid (words of a row / 256, rows, images)
+__global__ void __launch_bounds__(256) k_grey(const uint8_t *__restrict__ rgb, int rgb_pitch, uint8_t *__restrict__ grey,
+                                              int pitch, int h, int w)
 {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (; i < quads; i += stride) {
-        uint32_t a = __ldg(rgb + 3 * i), b = __ldg(rgb + 3 * i + 1), c = __ldg(rgb + 3 * i + 2);
-        uint32_t p0 = luma_q15(a & 255, (a >> 8) & 255, (a >> 16) & 255);
-        uint32_t p1 = luma_q15(a >> 24, b & 255, (b >> 8) & 255);
-        uint32_t p2 = luma_q15((b >> 16) & 255, b >> 24, c & 255);
-        uint32_t p3 = luma_q15((c >> 8) & 255, (c >> 16) & 255, c >> 24);
-        grey[i] = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+    if (x >= w) return;
+    const uint8_t *src = rgb + ((size_t)blockIdx.z * h + y) * rgb_pitch + (size_t)x * 3;
+    uint8_t *dst = grey + ((size_t)blockIdx.z * h + y) * pitch;
+    const bool al_in = ((reinterpret_cast<uintptr_t>(rgb) | (uintptr_t)rgb_pitch) & 3) == 0;
+    const bool al_out = ((reinterpret_cast<uintptr_t>(grey) | (uintptr_t)pitch) & 3) == 0;
+    uint32_t out = 0;
+    if (al_in && x + 3 < w) {
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(src);
+        const uint32_t a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+        out = luma_q15(a & 255, (a >> 8) & 255, (a >> 16) & 255) | (luma_q15(a >> 24, b & 255, (b >> 8) & 255) << 8) |
+              (luma_q15((b >> 16) & 255, b >> 24, c & 255) << 16) | (luma_q15((c >> 8) & 255, (c >> 16) & 255, c >> 24) << 24);
+    } else {
+        for (int k = 0; k < 4 && x + k < w; k++) out |= luma_q15(src[3 * k], src[3 * k + 1], src[3 * k + 2]) << (8 * k);
     }
+    store4(dst, x, w, write_limit(w, pitch, 4), al_out, out);
 }
 
-__global__ void __launch_bounds__(256) k_grey1(const uint8_t *__restrict__ rgb, uint8_t *__restrict__ grey,
-                                               size_t first, size_t total)
+// ------------------------------------------------------------------ contrast + brightness (A.9)
+// PIL: ImageEnhance.Contrast(img).enhance(fc) = blend(solid(m), img, fc), m = int(mean(L) + 0.5) with
+// L = (19595 R + 38470 G + 7471 B + 0x8000) >> 16; ImageEnhance.Brightness(img).enhance(fb) =
+// blend(black, img, fb).  ImagingBlend computes, per channel value, t = a + f * (b - a) in float32 and
+// stores 0 if t <= 0, 255 if t >= 255, else trunc(t) -- so both steps are 256-entry tables per image.
+__global__ void __launch_bounds__(256) k_luma_sum(const MapSet ms, const Dims dims, int ch, unsigned long long *sums)
 {
-    size_t i = first + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (; i < total; i += stride)
-        grey[i] = (uint8_t)luma_q15(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
-}
-
-// ------------------------------------------------------------------ contrast (A.9)
-__global__ void __launch_bounds__(256) k_luma_sum(const uint8_t *__restrict__ rgb, unsigned long long *sums,
-                                                  int h, int w)
-{
-    const uint8_t *img = rgb + (size_t)blockIdx.y * h * w * 3;
-    size_t px = (size_t)h * w;
+    const int img_i = blockIdx.y;
+    const int2 wh = dims.of(img_i);
+    int pitch;
+    const uint8_t *img = ms.plane(img_i, pitch);
     unsigned long long s = 0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < px; i += (size_t)gridDim.x * blockDim.x)
-        s += (19595u * img[3 * i] + 38470u * img[3 * i + 1] + 7471u * img[3 * i + 2] + 0x8000u) >> 16;
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0 && s) atomicAdd(sums + blockIdx.y, s);
-}
-
-__global__ void __launch_bounds__(256) k_contrast(const uint8_t *__restrict__ rgb, uint8_t *__restrict__ out,
-                                                  const unsigned long long *sums, int h, int w, float f)
-{
-    size_t px = (size_t)h * w;
-    int m = (int)((double)sums[blockIdx.y] / (double)px + 0.5);
-    float fm = (float)m;
-    const uint8_t *img = rgb + (size_t)blockIdx.y * px * 3;
-    uint8_t *o = out + (size_t)blockIdx.y * px * 3;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < 3 * px; i += (size_t)gridDim.x * blockDim.x) {
-        float t = __fadd_rn(fm, __fmul_rn(f, __fsub_rn((float)img[i], fm)));
-        o[i] = t <= 0.f ? 0 : (t >= 255.f ? 255 : (uint8_t)t);
+    for (int y = blockIdx.x; y < wh.y; y += gridDim.x) {
+        const uint8_t *row = img + (size_t)y * pitch;
+        if (ch == 1)         // a mode-"L" source converted to RGB has R = G = B = v, whose L is v
+            for (int x = threadIdx.x; x < wh.x; x += blockDim.x) s += row[x];
+        else
+            for (int x = threadIdx.x; x < wh.x; x += blockDim.x)
+                s += (19595u * row[3 * x] + 38470u * row[3 * x + 1] + 7471u * row[3 * x + 2] + 0x8000u) >> 16;
     }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(sums + img_i, s);
 }
 
-// ------------------------------------------------------------------ Gaussian 3/5/7 fused (A.2)
-// Output tile 128 x 32 per 256-thread block.  Input staged with a halo of 4 (x) / 3 (y),
-// REFLECT_101.  Horizontal pass keeps Q8 sums (<= 65280, u16) for the three kernels in
-// shared memory, vertical pass accumulates Q16 and rounds once.
-constexpr int GT_W = 128, GT_H = 32, GH_X = 16, GH_Y = 3;   // x halo 16: bulk-copy rows are 16-byte aligned
-constexpr int GS_W = GT_W + 2 * GH_X;   // 160
-constexpr int GS_H = GT_H + 2 * GH_Y;   // 38
-
-__global__ void __launch_bounds__(256) k_gauss357(const uint8_t *__restrict__ src, uint8_t *__restrict__ d3,
-                                                  uint8_t *__restrict__ d5, uint8_t *__restrict__ d7, int h, int w, bool al,
-                                                  bool bulk)
+__device__ __forceinline__ uint32_t blend_u8(float a, float f, uint32_t b)
 {
-    __shared__ __align__(128) uint8_t s_in[GS_H * GS_W];
-    __shared__ uint64_t s_bar;
-    __shared__ __align__(16) uint16_t s_h[3][GS_H][GT_W];
-    const size_t plane = (size_t)h * w;
-    const uint8_t *img = src + blockIdx.z * plane;
-    const int x0 = blockIdx.x * GT_W, y0 = blockIdx.y * GT_H;
-    stage_tile_bulk(s_in, img, h, w, x0 - GH_X, y0 - GH_Y, GS_W, GS_H, BORDER_REFLECT101, bulk, al, &s_bar);
-    for (int idx = threadIdx.x; idx < GS_H * GT_W; idx += blockDim.x) {
-        int ty = idx / GT_W, tx = idx - ty * GT_W;
-        const uint8_t *p = s_in + ty * GS_W + tx + GH_X;
-        int a0 = p[0], a1 = p[-1] + p[1], a2 = p[-2] + p[2], a3 = p[-3] + p[3];
-        s_h[0][ty][tx] = (uint16_t)(88 * a0 + 84 * a1);
-        s_h[1][ty][tx] = (uint16_t)(54 * a0 + 52 * a1 + 49 * a2);
-        s_h[2][ty][tx] = (uint16_t)(38 * a0 + 38 * a1 + 36 * a2 + 35 * a3);
+    const float t = __fadd_rn(a, __fmul_rn(f, __fsub_rn((float)b, a)));
+    return t <= 0.f ? 0u : (t >= 255.f ? 255u : (uint32_t)t);
+}
+
+__global__ void __launch_bounds__(256) k_enhance(const MapSet ms, const Dims dims, int ch, uint8_t *__restrict__ out, int opitch,
+                                                 size_t ostride, const unsigned long long *sums, float fc, float fb)
+{
+    __shared__ uint8_t s_lut[256];
+    const int img_i = blockIdx.y;
+    const int2 wh = dims.of(img_i);
+    int pitch;
+    const uint8_t *img = ms.plane(img_i, pitch);
+    uint8_t *o = out + (size_t)img_i * ostride;
+    {
+        const int m = (int)((double)sums[img_i] / (double)((long long)wh.x * wh.y) + 0.5);
+        const uint32_t c = fc == 1.0f ? threadIdx.x : blend_u8((float)m, fc, threadIdx.x);
+        s_lut[threadIdx.x] = (uint8_t)(fb == 1.0f ? c : blend_u8(0.0f, fb, c));
     }
     __syncthreads();
-    // each thread: 4 consecutive x of one row, all three kernels
-    for (int idx = threadIdx.x; idx < GT_H * (GT_W / 4); idx += blockDim.x) {
-        int ty = idx / (GT_W / 4), gx = (idx - ty * (GT_W / 4)) * 4;
-        int y = y0 + ty;
-        if (y >= h) continue;
-        uint32_t o3 = 0, o5 = 0, o7 = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            int tx = gx + k, r = ty + GH_Y;
-            uint32_t v3 = 88u * s_h[0][r][tx] + 84u * (s_h[0][r - 1][tx] + s_h[0][r + 1][tx]);
-            uint32_t v5 = 54u * s_h[1][r][tx] + 52u * (s_h[1][r - 1][tx] + s_h[1][r + 1][tx]) +
-                          49u * (s_h[1][r - 2][tx] + s_h[1][r + 2][tx]);
-            uint32_t v7 = 38u * s_h[2][r][tx] + 38u * (s_h[2][r - 1][tx] + s_h[2][r + 1][tx]) +
-                          36u * (s_h[2][r - 2][tx] + s_h[2][r + 2][tx]) +
-                          35u * (s_h[2][r - 3][tx] + s_h[2][r + 3][tx]);
-            o3 |= min((v3 + 32768u) >> 16, 255u) << (8 * k);
-            o5 |= min((v5 + 32768u) >> 16, 255u) << (8 * k);
-            o7 |= min((v7 + 32768u) >> 16, 255u) << (8 * k);
-        }
-        int x = x0 + gx;
-        size_t o = blockIdx.z * plane + (size_t)y * w + x;
-        if (al && x + 3 < w) {
-            if (d3) *reinterpret_cast<uint32_t *>(d3 + o) = o3;
-            if (d5) *reinterpret_cast<uint32_t *>(d5 + o) = o5;
-            if (d7) *reinterpret_cast<uint32_t *>(d7 + o) = o7;
-        } else {
-            for (int k = 0; k < 4 && x + k < w; k++) {
-                if (d3) d3[o + k] = (uint8_t)(o3 >> (8 * k));
-                if (d5) d5[o + k] = (uint8_t)(o5 >> (8 * k));
-                if (d7) d7[o + k] = (uint8_t)(o7 >> (8 * k));
-            }
-        }
+    for (int y = blockIdx.x; y < wh.y; y += gridDim.x) {
+        const uint8_t *row = img + (size_t)y * pitch;
+        uint8_t *orow = o + (size_t)y * opitch;
+        for (int x = threadIdx.x; x < ch * wh.x; x += blockDim.x) orow[x] = s_lut[row[x]];
     }
+}
+
+int enhance(const MapSet &ms, const Dims &dims, int ch, uint8_t *out, int opitch, size_t ostride, void *scratch8n, float fc,
+            float fb, cudaStream_t st)
+{
+    ScopedSection sec(SEC_ENHANCE, st);
+    unsigned long long *sums = (unsigned long long *)scratch8n;
+    I2S_CUDA(cudaMemsetAsync(sums, 0, sizeof(unsigned long long) * ms.n, st));
+    dim3 grid(min(dims.h, max(1, 8 * sm_count() / max(ms.n, 1))), ms.n);
+    if (fc != 1.0f) {
+        k_luma_sum<<<grid, 256, 0, st>>>(ms, dims, ch, sums);
+        I2S_CHECK_LAUNCH("k_luma_sum");
+    }
+    k_enhance<<<grid, 256, 0, st>>>(ms, dims, ch, out, opitch, ostride, sums, fc, fb);
+    I2S_CHECK_LAUNCH("k_enhance");
+    return I2S_OK;
+}
+
+// A single-channel source batch (any pitch / offsets) onto the library's canvas
+__global__ void __launch_bounds__(256) k_to_canvas(const MapSet ms, const Dims dims, uint8_t *__restrict__ out, int opitch,
+                                                   size_t ostride)
+{
+    const int img_i = blockIdx.y;
+    const int2 wh = dims.of(img_i);
+    int pitch;
+    const uint8_t *img = ms.plane(img_i, pitch);
+    uint8_t *o = out + (size_t)img_i * ostride;
+    for (int y = blockIdx.x; y < wh.y; y += gridDim.x)
+        for (int x = threadIdx.x; x < wh.x; x += blockDim.x) o[(size_t)y * opitch + x] = img[(size_t)y * pitch + x];
+}
+
+int to_canvas(const MapSet &ms, const Dims &dims, uint8_t *out, int opitch, size_t ostride, cudaStream_t st)
+{
+    ScopedSection sec(SEC_GREY, st);
+    dim3 grid(min(dims.h, max(1, 8 * sm_count() / max(ms.n, 1))), ms.n);
+    k_to_canvas<<<grid, 256, 0, st>>>(ms, dims, out, opitch, ostride);
+    I2S_CHECK_LAUNCH("k_to_canvas");
+    return I2S_OK;
 }
 
 // ------------------------------------------------------------------ Gaussian 3/5/7, register rolling (A.2)
@@ -174,27 +171,34 @@ __device__ __forceinline__ uint32_t load_word_border(const uint8_t *__restrict__
 }
 
 __global__ void __launch_bounds__(GR_WARPS * 32) k_gauss357_roll(const uint8_t *__restrict__ src, uint8_t *__restrict__ d3,
-                                                                 uint8_t *__restrict__ d5, uint8_t *__restrict__ d7, int h,
-                                                                 int w, bool al, int strips_x, int strips_y, int total)
+                                                                 uint8_t *__restrict__ d5, uint8_t *__restrict__ d7,
+                                                                 const Dims dims, int spitch, size_t sstride, int pitch,
+                                                                 size_t stride, int strips_x, int strips_y, int total)
 {
     const int lane = threadIdx.x & 31;
     const int strip = blockIdx.x * GR_WARPS + (threadIdx.x >> 5);
     if (strip >= total) return;                                // warp-uniform
     const int sx = strip % strips_x, t = strip / strips_x, sy = t % strips_y, img = t / strips_y;
-    const size_t plane = (size_t)h * w;
-    const uint8_t *im = src + img * plane;
+    const int2 wh = dims.of(img);
+    const int w = wh.x, h = wh.y;
+    if (sx * GR_OW >= w || sy * GR_TH >= h) return;            // strip outside this image (ragged batch)
+    const uint8_t *im = src + img * sstride;
+    const bool al = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)spitch | (uintptr_t)sstride) & 3) == 0;
+    const bool al_out = ((reinterpret_cast<uintptr_t>(d3) | reinterpret_cast<uintptr_t>(d5) | reinterpret_cast<uintptr_t>(d7) |
+                          (uintptr_t)pitch | (uintptr_t)stride) & 3) == 0;
+    const int wlim = write_limit(w, pitch, 4);
     const int x = sx * GR_OW - 4 + 4 * lane;
     const int y0 = sy * GR_TH, y1 = min(y0 + GR_TH, h);
     const bool store_lane = lane >= 1 && lane <= 30 && x < w;
-    uint32_t wl[7], wh[7];
+    uint32_t wl[7], wh7[7];
 #pragma unroll
     for (int k = 0; k < 6; k++) {
-        const uint32_t v = load_word_border(im + (size_t)border_index(y0 - 3 + k, h, BORDER_REFLECT101) * w, x, w, al,
+        const uint32_t v = load_word_border(im + (size_t)border_index(y0 - 3 + k, h, BORDER_REFLECT101) * spitch, x, w, al,
                                             BORDER_REFLECT101);
-        wl[k] = roll::pair_lo(v); wh[k] = roll::pair_hi(v);
+        wl[k] = roll::pair_lo(v); wh7[k] = roll::pair_hi(v);
     }
     // the row entering the window is loaded one iteration ahead of its use
-    uint32_t nxt = load_word_border(im + (size_t)border_index(y0 + 3, h, BORDER_REFLECT101) * w, x, w, al, BORDER_REFLECT101);
+    uint32_t nxt = load_word_border(im + (size_t)border_index(y0 + 3, h, BORDER_REFLECT101) * spitch, x, w, al, BORDER_REFLECT101);
 #pragma unroll 1
     for (int yb = y0; yb < y1; yb += 7) {
 #pragma unroll
@@ -202,13 +206,13 @@ __global__ void __launch_bounds__(GR_WARPS * 32) k_gauss357_roll(const uint8_t *
             const int y = yb + u;
             if (y < y1) {                                      // warp-uniform
                 const uint32_t v = nxt;
-                nxt = load_word_border(im + (size_t)border_index(y + 4, h, BORDER_REFLECT101) * w, x, w, al,
+                nxt = load_word_border(im + (size_t)border_index(y + 4, h, BORDER_REFLECT101) * spitch, x, w, al,
                                        BORDER_REFLECT101);
-                wl[(u + 6) % 7] = roll::pair_lo(v); wh[(u + 6) % 7] = roll::pair_hi(v);
+                wl[(u + 6) % 7] = roll::pair_lo(v); wh7[(u + 6) % 7] = roll::pair_hi(v);
                 const uint32_t rl[7] = {wl[u % 7], wl[(u + 1) % 7], wl[(u + 2) % 7], wl[(u + 3) % 7], wl[(u + 4) % 7],
                                         wl[(u + 5) % 7], wl[(u + 6) % 7]};
-                const uint32_t rh[7] = {wh[u % 7], wh[(u + 1) % 7], wh[(u + 2) % 7], wh[(u + 3) % 7], wh[(u + 4) % 7],
-                                        wh[(u + 5) % 7], wh[(u + 6) % 7]};
+                const uint32_t rh[7] = {wh7[u % 7], wh7[(u + 1) % 7], wh7[(u + 2) % 7], wh7[(u + 3) % 7], wh7[(u + 4) % 7],
+                                        wh7[(u + 5) % 7], wh7[(u + 6) % 7]};
                 uint32_t V[6];
                 roll::gauss_vertical(rl, rh, V);
                 // neighbour pairs: left lane's (V2,V3) [and (V0,V1) for the 7-tap], right lane's (V0,V1) [and (V2,V3)]
@@ -217,35 +221,36 @@ __global__ void __launch_bounds__(GR_WARPS * 32) k_gauss357_roll(const uint8_t *
                 const uint32_t l7 = __shfl_up_sync(0xffffffffu, V[5], 1), r7 = __shfl_down_sync(0xffffffffu, V[4], 1);
                 const uint32_t ll7 = __shfl_up_sync(0xffffffffu, V[4], 1), rr7 = __shfl_down_sync(0xffffffffu, V[5], 1);
                 if (store_lane) {
-                    const uint32_t o3 = roll::gauss_h3(l3, V[0], V[1], r3);
-                    const uint32_t o5 = roll::gauss_h5(l5, V[2], V[3], r5);
-                    const uint32_t o7 = roll::gauss_h7(ll7, l7, V[4], V[5], r7, rr7);
-                    const size_t o = img * plane + (size_t)y * w + x;
-                    if (al) {
-                        if (d3) *reinterpret_cast<uint32_t *>(d3 + o) = o3;
-                        if (d5) *reinterpret_cast<uint32_t *>(d5 + o) = o5;
-                        if (d7) *reinterpret_cast<uint32_t *>(d7 + o) = o7;
-                    } else {
-                        for (int k = 0; k < 4 && x + k < w; k++) {
-                            if (d3) d3[o + k] = (uint8_t)(o3 >> (8 * k));
-                            if (d5) d5[o + k] = (uint8_t)(o5 >> (8 * k));
-                            if (d7) d7[o + k] = (uint8_t)(o7 >> (8 * k));
-                        }
-                    }
+                    const size_t o = img * stride + (size_t)y * pitch;
+                    if (d3) store4(d3 + o, x, w, wlim, al_out, roll::gauss_h3(l3, V[0], V[1], r3));
+                    if (d5) store4(d5 + o, x, w, wlim, al_out, roll::gauss_h5(l5, V[2], V[3], r5));
+                    if (d7) store4(d7 + o, x, w, wlim, al_out, roll::gauss_h7(ll7, l7, V[4], V[5], r7, rr7));
                 }
             }
         }
     }
 }
 
+int gauss357(const uint8_t *src, int spitch, size_t sstride, uint8_t *d3, uint8_t *d5, uint8_t *d7, int pitch, size_t stride,
+             const Dims &dims, int n, cudaStream_t st)
+{
+    ScopedSection sec(SEC_GAUSS, st);
+    const int strips_x = cdiv(dims.w, GR_OW), strips_y = cdiv(dims.h, GR_TH);
+    const long long total = (long long)n * strips_x * strips_y;
+    I2S_ARG(total < (1ll << 31));
+    k_gauss357_roll<<<(unsigned)((total + GR_WARPS - 1) / GR_WARPS), GR_WARPS * 32, 0, st>>>(src, d3, d5, d7, dims, spitch, sstride,
+                                                                                            pitch, stride, strips_x, strips_y, (int)total);
+    I2S_CHECK_LAUNCH("k_gauss357_roll");
+    return I2S_OK;
+}
+
 // ------------------------------------------------------------------ median (A.3)
 // Exact b x b median with BORDER_REPLICATE by bit-sliced rank selection.  The staged tile is
-// transposed once per block into eight 1-bit planes (warp ballots).  A thread then gathers, for each
-// plane, the window bits of its four adjacent output pixels (b rows x (b+3) columns, rows packed at
+// transposed once per block into eight 1-bit planes.  A thread then gathers, for each plane, the
+// window bits of its four adjacent output pixels (b rows x (b+3) columns, rows packed at
 // a stride of b+3 bits) and selects the median MSB-first: with C the set of still-possible window
 // elements and k the rank wanted inside C, the next result bit is 0 iff k < popc(C & ~plane), which
-// also narrows C.  Cost is independent of the image content: 8 rounds of a few logic ops and
-// popcounts per pixel, no sorting network, no histogram.
+// also narrows C.  No sorting network, no histogram.
 constexpr int MT_W = 64, MT_H = 32;
 
 // Median of the B x B windows of 4 adjacent pixels (row ty, columns gx..gx+3 of the tile) from the bit
@@ -337,8 +342,8 @@ __device__ __forceinline__ uint32_t median4_planes(const uint32_t (&s_bits)[10][
 // bit 0 -> 3x3 into dst3, bit 1 -> 5x5 into dst5, bit 2 -> 7x7 into dst7.
 template <int MASK> __global__ void __launch_bounds__(256, 4) k_median(const uint8_t *__restrict__ src,
                                                                     uint8_t *__restrict__ dst3, uint8_t *__restrict__ dst5,
-                                                                    uint8_t *__restrict__ dst7, int h, int w, bool al,
-                                                                    bool bulk)
+                                                                    uint8_t *__restrict__ dst7, const Dims dims, int spitch,
+                                                                    size_t sstride, int pitch, size_t stride)
 {
     constexpr int RS = (MASK & 4) ? 3 : (MASK & 2) ? 2 : 1, HX = 16;   // x halo 16: bulk-copy rows are 16-byte aligned
     constexpr int SW = MT_W + 2 * HX, SH = MT_H + 2 * RS;
@@ -346,11 +351,18 @@ template <int MASK> __global__ void __launch_bounds__(256, 4) k_median(const uin
     __shared__ __align__(128) uint8_t s_in[SH * SW];
     __shared__ uint32_t s_bits[10][SH][GW + 1];      // planes 0..7: bits of the pixel; 8: pixel == 255; 9: pixel == 0
     __shared__ uint64_t s_bar;
-    const size_t plane = (size_t)h * w;
-    const uint8_t *img = src + blockIdx.z * plane;
+    const int2 wh = dims.of(blockIdx.z);
+    const int w = wh.x, h = wh.y;
     const int x0 = blockIdx.x * MT_W, y0 = blockIdx.y * MT_H;
+    if (x0 >= w || y0 >= h) return;                  // tile outside this image (ragged batch)
+    const uint8_t *img = src + blockIdx.z * sstride;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    stage_tile_bulk(s_in, img, h, w, x0 - HX, y0 - RS, SW, SH, BORDER_REPLICATE, bulk, al, &s_bar);
+    const uintptr_t src_al = reinterpret_cast<uintptr_t>(src) | (uintptr_t)spitch | (uintptr_t)sstride;
+    const bool al_in = (src_al & 3) == 0, bulk = (src_al & 15) == 0;
+    const bool al = ((reinterpret_cast<uintptr_t>(dst3) | reinterpret_cast<uintptr_t>(dst5) | reinterpret_cast<uintptr_t>(dst7) |
+                      (uintptr_t)pitch | (uintptr_t)stride) & 3) == 0;
+    const int wlim = write_limit(w, pitch, 4);
+    stage_tile_bulk(s_in, img, h, w, spitch, x0 - HX, y0 - RS, SW, SH, BORDER_REPLICATE, bulk, al_in, &s_bar);
     {   // bit planes: s_bits[b][row][g] bit i = bit b of tile pixel (row, 32 g + i).  A thread turns
         // 8 adjacent pixels into one byte of every plane: bit b of the 4 bytes of a word is gathered
         // into a nibble by one multiply ((x & 0x01010101) * 0x01020408 puts byte j's bit at 24 + j).
@@ -377,22 +389,15 @@ template <int MASK> __global__ void __launch_bounds__(256, 4) k_median(const uin
         const int ty = (q / (MT_W / 16)) * 8 + (lane >> 2), gx = ((q % (MT_W / 16)) * 4 + (lane & 3)) * 4;
         const int y = y0 + ty, x = x0 + gx;
         const bool live = y < h && x < w;
-        const size_t o = blockIdx.z * plane + (size_t)y * w + x;
-        auto store4 = [&](uint8_t *dst, uint32_t packed) {
-            if (!live) return;
-            if (al && x + 3 < w) *reinterpret_cast<uint32_t *>(dst + o) = packed;
-            else
-                for (int k2 = 0; k2 < 4 && x + k2 < w; k2++) dst[o + k2] = (uint8_t)(packed >> (8 * k2));
-        };
-        if (MASK & 4) store4(dst7, median4_planes<7, RS, HX, SH, GW>(s_bits, ty, gx, live));
-        if (MASK & 2) store4(dst5, median4_planes<5, RS, HX, SH, GW>(s_bits, ty, gx, live));
-        if (MASK & 1) store4(dst3, median4_planes<3, RS, HX, SH, GW>(s_bits, ty, gx, live));
+        const size_t o = blockIdx.z * stride + (size_t)y * pitch;
+        if (MASK & 4) { const uint32_t v = median4_planes<7, RS, HX, SH, GW>(s_bits, ty, gx, live); if (live) store4(dst7 + o, x, w, wlim, al, v); }
+        if (MASK & 2) { const uint32_t v = median4_planes<5, RS, HX, SH, GW>(s_bits, ty, gx, live); if (live) store4(dst5 + o, x, w, wlim, al, v); }
+        if (MASK & 1) { const uint32_t v = median4_planes<3, RS, HX, SH, GW>(s_bits, ty, gx, live); if (live) store4(dst3 + o, x, w, wlim, al, v); }
     }
 }
 
-// ---- 3x3 and 5x5: minimum-exchange selection networks on two pixels per register
-// (19 exchanges for 9 inputs, 99 for 25 inputs; N. Devillard's opt_med9 / opt_med25 orderings,
-// checked exhaustively with the 0-1 principle).  An exchange is one VIMNMX.U16x2 min + one max.
+// ---- a lone 3x3: 19-exchange selection network on two pixels per register (N. Devillard's opt_med9
+// ordering, checked exhaustively with the 0-1 principle).  An exchange is one VIMNMX.U16x2 min + one max.
 __device__ __forceinline__ void cex(uint32_t &a, uint32_t &b)
 {
     uint32_t lo = __vminu2(a, b);
@@ -409,42 +414,24 @@ __device__ __forceinline__ uint32_t net_median9(uint32_t (&p)[9])
     return p[4];
 }
 
-__device__ __forceinline__ uint32_t net_median25(uint32_t (&p)[25])
+__global__ void __launch_bounds__(256) k_median3_net(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                                     const Dims dims, int spitch, size_t sstride, int pitch, size_t stride)
 {
-    cex(p[0], p[1]); cex(p[3], p[4]); cex(p[2], p[4]); cex(p[2], p[3]); cex(p[6], p[7]); cex(p[5], p[7]);
-    cex(p[5], p[6]); cex(p[9], p[10]); cex(p[8], p[10]); cex(p[8], p[9]); cex(p[12], p[13]); cex(p[11], p[13]);
-    cex(p[11], p[12]); cex(p[15], p[16]); cex(p[14], p[16]); cex(p[14], p[15]); cex(p[18], p[19]); cex(p[17], p[19]);
-    cex(p[17], p[18]); cex(p[21], p[22]); cex(p[20], p[22]); cex(p[20], p[21]); cex(p[23], p[24]); cex(p[2], p[5]);
-    cex(p[3], p[6]); cex(p[0], p[6]); cex(p[0], p[3]); cex(p[4], p[7]); cex(p[1], p[7]); cex(p[1], p[4]);
-    cex(p[11], p[14]); cex(p[8], p[14]); cex(p[8], p[11]); cex(p[12], p[15]); cex(p[9], p[15]); cex(p[9], p[12]);
-    cex(p[13], p[16]); cex(p[10], p[16]); cex(p[10], p[13]); cex(p[20], p[23]); cex(p[17], p[23]); cex(p[17], p[20]);
-    cex(p[21], p[24]); cex(p[18], p[24]); cex(p[18], p[21]); cex(p[19], p[22]); cex(p[8], p[17]); cex(p[9], p[18]);
-    cex(p[0], p[18]); cex(p[0], p[9]); cex(p[10], p[19]); cex(p[1], p[19]); cex(p[1], p[10]); cex(p[11], p[20]);
-    cex(p[2], p[20]); cex(p[2], p[11]); cex(p[12], p[21]); cex(p[3], p[21]); cex(p[3], p[12]); cex(p[13], p[22]);
-    cex(p[4], p[22]); cex(p[4], p[13]); cex(p[14], p[23]); cex(p[5], p[23]); cex(p[5], p[14]); cex(p[15], p[24]);
-    cex(p[6], p[24]); cex(p[6], p[15]); cex(p[7], p[16]); cex(p[7], p[19]); cex(p[13], p[21]); cex(p[15], p[23]);
-    cex(p[7], p[13]); cex(p[7], p[15]); cex(p[1], p[9]); cex(p[3], p[11]); cex(p[5], p[17]); cex(p[11], p[17]);
-    cex(p[9], p[17]); cex(p[4], p[10]); cex(p[6], p[12]); cex(p[7], p[14]); cex(p[4], p[6]); cex(p[4], p[7]);
-    cex(p[12], p[14]); cex(p[10], p[14]); cex(p[6], p[7]); cex(p[10], p[12]); cex(p[6], p[10]); cex(p[6], p[17]);
-    cex(p[12], p[17]); cex(p[7], p[17]); cex(p[7], p[10]); cex(p[12], p[18]); cex(p[7], p[12]); cex(p[10], p[18]);
-    cex(p[12], p[20]); cex(p[10], p[20]); cex(p[10], p[12]);
-    return p[12];
-}
-
-template <int B> __global__ void __launch_bounds__(256) k_median_net(const uint8_t *__restrict__ src,
-                                                                     uint8_t *__restrict__ dst, int h, int w, bool al,
-                                                                     bool bulk)
-{
-    static_assert(B == 3 || B == 5, "selection networks exist for 3x3 and 5x5");
-    constexpr int R = B / 2, HX = 16;
+    constexpr int B = 3, R = 1, HX = 16;
     constexpr int SW = MT_W + 2 * HX, SH = MT_H + 2 * R;
     __shared__ __align__(128) uint8_t s_in[SH * SW];
     __shared__ uint64_t s_bar;
-    const size_t plane = (size_t)h * w;
-    const uint8_t *img = src + blockIdx.z * plane;
-    uint8_t *out = dst + blockIdx.z * plane;
+    const int2 wh = dims.of(blockIdx.z);
+    const int w = wh.x, h = wh.y;
     const int x0 = blockIdx.x * MT_W, y0 = blockIdx.y * MT_H;
-    stage_tile_bulk(s_in, img, h, w, x0 - HX, y0 - R, SW, SH, BORDER_REPLICATE, bulk, al, &s_bar);
+    if (x0 >= w || y0 >= h) return;
+    const uint8_t *img = src + blockIdx.z * sstride;
+    uint8_t *out = dst + blockIdx.z * stride;
+    const uintptr_t src_al = reinterpret_cast<uintptr_t>(src) | (uintptr_t)spitch | (uintptr_t)sstride;
+    const bool al_in = (src_al & 3) == 0, bulk = (src_al & 15) == 0;
+    const bool al = ((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)pitch | (uintptr_t)stride) & 3) == 0;
+    const int wlim = write_limit(w, pitch, 4);
+    stage_tile_bulk(s_in, img, h, w, spitch, x0 - HX, y0 - R, SW, SH, BORDER_REPLICATE, bulk, al_in, &s_bar);
     for (int idx = threadIdx.x; idx < MT_H * (MT_W / 4); idx += blockDim.x) {
         int ty = idx / (MT_W / 4), gx = (idx - ty * (MT_W / 4)) * 4;
         int y = y0 + ty, x = x0 + gx;
@@ -467,22 +454,28 @@ template <int B> __global__ void __launch_bounds__(256) k_median_net(const uint8
                 e[dy][k] = (off & 1) ? __funnelshift_r(X[off >> 1], X[(off >> 1) + 1], 16) : X[off >> 1];
             }
         }
-        uint32_t pa, pb;
-        {
-            uint32_t p[B * B], q[B * B];
+        uint32_t p[9], q[9];
 #pragma unroll
-            for (int dy = 0; dy < B; dy++)
+        for (int dy = 0; dy < B; dy++)
 #pragma unroll
-                for (int dx = 0; dx < B; dx++) { p[dy * B + dx] = e[dy][dx]; q[dy * B + dx] = e[dy][dx + 2]; }
-            if (B == 3) { pa = net_median9(reinterpret_cast<uint32_t (&)[9]>(p)); pb = net_median9(reinterpret_cast<uint32_t (&)[9]>(q)); }
-            else { pa = net_median25(reinterpret_cast<uint32_t (&)[25]>(p)); pb = net_median25(reinterpret_cast<uint32_t (&)[25]>(q)); }
-        }
-        uint32_t packed = (pa & 0xffu) | ((pa >> 8) & 0xff00u) | ((pb & 0xffu) << 16) | ((pb << 8) & 0xff000000u);
-        size_t o = (size_t)y * w + x;
-        if (al && x + 3 < w) *reinterpret_cast<uint32_t *>(out + o) = packed;
-        else
-            for (int k2 = 0; k2 < 4 && x + k2 < w; k2++) out[o + k2] = (uint8_t)(packed >> (8 * k2));
+            for (int dx = 0; dx < B; dx++) { p[dy * B + dx] = e[dy][dx]; q[dy * B + dx] = e[dy][dx + 2]; }
+        const uint32_t pa = net_median9(p), pb = net_median9(q);
+        const uint32_t packed = (pa & 0xffu) | ((pa >> 8) & 0xff00u) | ((pb & 0xffu) << 16) | ((pb << 8) & 0xff000000u);
+        store4(out + (size_t)y * pitch, x, w, wlim, al, packed);
     }
+}
+
+// medianBlur 3, 5 and 7 of the same images from one staged tile and one set of bit planes (the blur
+// pyramid of img2sgf.py:171-175 needs all three).
+int median357(const uint8_t *src, int spitch, size_t sstride, uint8_t *d3, uint8_t *d5, uint8_t *d7, int pitch, size_t stride,
+              const Dims &dims, int n, cudaStream_t st)
+{
+    if (n == 0) return I2S_OK;
+    dim3 grid(cdiv(dims.w, MT_W), cdiv(dims.h, MT_H), n);
+    ScopedSection sec(SEC_MEDIAN, st);
+    k_median<7><<<grid, 256, 0, st>>>(src, d3, d5, d7, dims, spitch, sstride, pitch, stride);
+    I2S_CHECK_LAUNCH("k_median");
+    return I2S_OK;
 }
 
 }  // namespace i2s
@@ -490,7 +483,8 @@ template <int B> __global__ void __launch_bounds__(256) k_median_net(const uint8
 using namespace i2s;
 
 extern "C" const char *i2s_last_error(void) { return i2s::g_err; }
-extern "C" int i2s_version(void) { return 100; }
+extern "C" int i2s_version(void) { return 200; }
+extern "C" int i2s_canvas_pitch(int w) { return w > 0 ? i2s::canvas_pitch(w) : 0; }
 extern "C" void i2s_default_limits(i2s_limits_t *lim)
 {
     lim->cand_cap = 4096;
@@ -498,108 +492,69 @@ extern "C" void i2s_default_limits(i2s_limits_t *lim)
     lim->line_cap = 1024;
     lim->hyst_passes = 5;
 }
-
-extern "C" int i2s_grey(const uint8_t *rgb, uint8_t *grey, int n, int h, int w, void *stream)
+extern "C" void i2s_default_params(i2s_params_t *p)
 {
-    I2S_ARG(rgb && grey && n >= 0 && h > 0 && w > 0);
+    p->line_threshold = 0;          // choose_threshold() per image, img2sgf.py:606-613,638
+    p->black_threshold = 128;       // :45
+    p->canny_low = 50;              // :47
+    p->canny_high = 200;            // :48
+    p->contrast_factor = 1.0f;      // input already enhanced
+    p->brightness_factor = 1.0f;
+}
+
+extern "C" int i2s_grey(const uint8_t *rgb, int rgb_pitch, uint8_t *grey, int pitch, int n, int h, int w, void *stream)
+{
+    I2S_ARG(rgb && grey && n >= 0 && h > 0 && w > 0 && h < 65536 && n < 65536);
+    if (rgb_pitch == 0) rgb_pitch = 3 * w;
+    if (pitch == 0) pitch = w;
+    I2S_ARG(rgb_pitch >= 3 * w && pitch >= w);
     if (n == 0) return I2S_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    size_t total = (size_t)n * h * w;
-    bool al = ((uintptr_t)rgb & 3) == 0 && ((uintptr_t)grey & 3) == 0;
-    size_t quads = al ? total / 4 : 0;
     ScopedSection sec(SEC_GREY, st);
-    if (quads) {
-        int blocks = (int)min((size_t)148 * 16, (quads + 255) / 256);
-        k_grey4<<<blocks, 256, 0, st>>>((const uint32_t *)rgb, (uint32_t *)grey, quads);
-        I2S_CHECK_LAUNCH("k_grey4");
-    }
-    if (quads * 4 < total) {
-        size_t rest = total - quads * 4;
-        int blocks = (int)min((size_t)148 * 16, (rest + 255) / 256);
-        k_grey1<<<blocks, 256, 0, st>>>(rgb, grey, quads * 4, total);
-        I2S_CHECK_LAUNCH("k_grey1");
-    }
+    k_grey<<<dim3(cdiv(cdiv(w, 4), 256), h, n), 256, 0, st>>>(rgb, rgb_pitch, grey, pitch, h, w);
+    I2S_CHECK_LAUNCH("k_grey");
     return I2S_OK;
 }
 
-extern "C" int i2s_contrast(const uint8_t *rgb, uint8_t *out, void *scratch8n, int n, int h, int w, double factor,
-                            void *stream)
+extern "C" int i2s_enhance(const uint8_t *rgb, int rgb_pitch, uint8_t *out, int out_pitch, void *scratch8n, int n, int h,
+                           int w, double contrast_factor, double brightness_factor, void *stream)
 {
-    I2S_ARG(rgb && out && scratch8n && n >= 0 && h > 0 && w > 0);
+    I2S_ARG(rgb && out && scratch8n && n >= 0 && h > 0 && w > 0 && n < 65536);
+    if (rgb_pitch == 0) rgb_pitch = 3 * w;
+    if (out_pitch == 0) out_pitch = 3 * w;
+    I2S_ARG(rgb_pitch >= 3 * w && out_pitch >= 3 * w);
     if (n == 0) return I2S_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    unsigned long long *sums = (unsigned long long *)scratch8n;
-    I2S_CUDA(cudaMemsetAsync(sums, 0, sizeof(unsigned long long) * n, st));
-    dim3 grid(min(cdiv(h * w, 256 * 8), 148 * 4), n);
-    k_luma_sum<<<grid, 256, 0, st>>>(rgb, sums, h, w);
-    I2S_CHECK_LAUNCH("k_luma_sum");
-    k_contrast<<<grid, 256, 0, st>>>(rgb, out, sums, h, w, (float)factor);
-    I2S_CHECK_LAUNCH("k_contrast");
-    return I2S_OK;
+    MapSet ms = MapSet::single(rgb, rgb_pitch, h, n);
+    return enhance(ms, Dims::uniform(h, w), 3, out, out_pitch, (size_t)h * out_pitch, scratch8n, (float)contrast_factor,
+                   (float)brightness_factor, (cudaStream_t)stream);
 }
 
 extern "C" int i2s_gauss357(const uint8_t *src, uint8_t *dst3, uint8_t *dst5, uint8_t *dst7, int n, int h, int w,
-                            void *stream)
+                            int pitch, void *stream)
 {
     I2S_ARG(src && n >= 0 && h > 0 && w > 0);
+    if (pitch == 0) pitch = w;
+    I2S_ARG(pitch >= w);
     if (n == 0) return I2S_OK;
-    bool al = (w & 3) == 0 && (((uintptr_t)src | (uintptr_t)dst3 | (uintptr_t)dst5 | (uintptr_t)dst7) & 3) == 0;
-    ScopedSection sec(SEC_GAUSS, (cudaStream_t)stream);
-    if (legacy_enabled("gauss")) {
-        dim3 grid(cdiv(w, GT_W), cdiv(h, GT_H), n);
-        bool bulk = (w & 15) == 0 && ((uintptr_t)src & 15) == 0;
-        k_gauss357<<<grid, 256, 0, (cudaStream_t)stream>>>(src, dst3, dst5, dst7, h, w, al, bulk);
-    } else {
-        const int strips_x = cdiv(w, GR_OW), strips_y = cdiv(h, GR_TH);
-        const long long total = (long long)n * strips_x * strips_y;
-        I2S_ARG(total < (1ll << 31));
-        k_gauss357_roll<<<(unsigned)((total + GR_WARPS - 1) / GR_WARPS), GR_WARPS * 32, 0, (cudaStream_t)stream>>>(
-            src, dst3, dst5, dst7, h, w, al, strips_x, strips_y, (int)total);
-    }
-    I2S_CHECK_LAUNCH("k_gauss357");
-    return I2S_OK;
+    return gauss357(src, pitch, (size_t)h * pitch, dst3, dst5, dst7, pitch, (size_t)h * pitch, Dims::uniform(h, w), n,
+                    (cudaStream_t)stream);
 }
 
-// medianBlur 3, 5 and 7 of the same images from one staged tile and one set of bit planes (the blur
-// pyramid of img2sgf.py:171-175 needs all three).  Internal to the library (find_circles).
-int i2s::median357(const uint8_t *src, uint8_t *d3, uint8_t *d5, uint8_t *d7, int n, int h, int w, cudaStream_t st)
+extern "C" int i2s_median(const uint8_t *src, uint8_t *dst, int n, int h, int w, int pitch, int b, void *stream)
 {
-    if (n == 0) return I2S_OK;
-    if (legacy_enabled("med357")) {
-        int rc;
-        if ((rc = i2s_median(src, d3, n, h, w, 3, st))) return rc;
-        if ((rc = i2s_median(src, d5, n, h, w, 5, st))) return rc;
-        return i2s_median(src, d7, n, h, w, 7, st);
-    }
-    dim3 grid(cdiv(w, MT_W), cdiv(h, MT_H), n);
-    ScopedSection sec(SEC_MEDIAN, st);
-    bool al = (w & 3) == 0 && (((uintptr_t)src | (uintptr_t)d3 | (uintptr_t)d5 | (uintptr_t)d7) & 3) == 0;
-    bool bulk = (w & 15) == 0 && ((uintptr_t)src & 15) == 0;
-    k_median<7><<<grid, 256, 0, st>>>(src, d3, d5, d7, h, w, al, bulk);
-    I2S_CHECK_LAUNCH("k_median");
-    return I2S_OK;
-}
-
-extern "C" int i2s_median(const uint8_t *src, uint8_t *dst, int n, int h, int w, int b, void *stream)
-{
-    I2S_ARG(src && dst && n >= 0 && h > 0 && w > 0 && (b == 1 || b == 3 || b == 5 || b == 7));
+    I2S_ARG(src && dst && n >= 0 && n < 65536 && h > 0 && w > 0 && (b == 1 || b == 3 || b == 5 || b == 7));
+    if (pitch == 0) pitch = w;
+    I2S_ARG(pitch >= w);
     if (n == 0) return I2S_OK;
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid(cdiv(w, MT_W), cdiv(h, MT_H), n);
+    const Dims dims = Dims::uniform(h, w);
+    const size_t stride = (size_t)h * pitch;
     ScopedSection sec(SEC_MEDIAN, st);
-    bool al = (w & 3) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 3) == 0;
-    bool bulk = (w & 15) == 0 && ((uintptr_t)src & 15) == 0;
-    if (b == 1) {
-        I2S_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * h * w, cudaMemcpyDeviceToDevice, st));
-    } else if (b == 3) {
-        k_median_net<3><<<grid, 256, 0, st>>>(src, dst, h, w, al, bulk);
-    } else if (b == 5) {
-        // bit planes + saturated-window shortcut beat the 99-exchange network on diagram content
-        if (legacy_enabled("med5net")) k_median_net<5><<<grid, 256, 0, st>>>(src, dst, h, w, al, bulk);
-        else k_median<2><<<grid, 256, 0, st>>>(src, nullptr, dst, nullptr, h, w, al, bulk);
-    } else {
-        k_median<4><<<grid, 256, 0, st>>>(src, nullptr, nullptr, dst, h, w, al, bulk);
-    }
+    if (b == 1) I2S_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * stride, cudaMemcpyDeviceToDevice, st));
+    else if (b == 3) k_median3_net<<<grid, 256, 0, st>>>(src, dst, dims, pitch, stride, pitch, stride);
+    else if (b == 5) k_median<2><<<grid, 256, 0, st>>>(src, nullptr, dst, nullptr, dims, pitch, stride, pitch, stride);
+    else k_median<4><<<grid, 256, 0, st>>>(src, nullptr, nullptr, dst, dims, pitch, stride, pitch, stride);
     I2S_CHECK_LAUNCH("k_median");
     return I2S_OK;
 }

@@ -8,7 +8,7 @@
 namespace i2s {
 
 static const char *kNames[SEC_COUNT] = {
-    "grey", "sobel_nms", "hysteresis", "state_to_edges", "gauss357", "median", "acc_clear", "edge_list", "vote", "peaks",
+    "grey", "enhance", "sobel_nms_rgb", "sobel_nms", "hysteresis", "state_to_edges", "gauss357", "median", "edge_list", "vote",
     "radius", "circles_finish", "stack", "mask", "line_vote", "line_peaks", "cluster", "validate", "classify"};
 
 struct Pair { cudaEvent_t a, b; int id; };

@@ -6,8 +6,8 @@
 namespace i2s {
 
 enum Section {
-    SEC_GREY = 0, SEC_SOBEL_NMS, SEC_HYSTERESIS, SEC_STATE_TO_EDGES, SEC_GAUSS, SEC_MEDIAN, SEC_ACC_CLEAR,
-    SEC_EDGE_LIST, SEC_VOTE, SEC_PEAKS, SEC_RADIUS, SEC_CIRCLES_FINISH, SEC_STACK, SEC_MASK, SEC_LINE_VOTE, SEC_LINE_PEAKS,
+    SEC_GREY = 0, SEC_ENHANCE, SEC_SOBEL_NMS_RGB, SEC_SOBEL_NMS, SEC_HYSTERESIS, SEC_STATE_TO_EDGES, SEC_GAUSS, SEC_MEDIAN,
+    SEC_EDGE_LIST, SEC_VOTE, SEC_RADIUS, SEC_CIRCLES_FINISH, SEC_STACK, SEC_MASK, SEC_LINE_VOTE, SEC_LINE_PEAKS,
     SEC_CLUSTER, SEC_VALIDATE, SEC_CLASSIFY, SEC_COUNT
 };
 

@@ -1,6 +1,6 @@
 // tma.cuh -- shared-memory tile staging with the bulk-copy engine (cp.async.bulk, SASS UBLKCP) and an
 // mbarrier, falling back to ordinary loads for tiles that touch the left/right image border or when
-// the image pitch is not 16-byte friendly (the reference fixtures have arbitrary widths).
+// a caller-provided plane is not 16-byte aligned / pitched.
 #pragma once
 #include "common.cuh"
 
@@ -46,14 +46,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     __trap();
 }
 
+// Orders earlier generic-proxy accesses to shared memory (ordinary loads/stores/atomics) before later
+// async-proxy writes to the same bytes (a bulk copy landing in a buffer the block has just used).
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // Stage a (tw x th) byte tile whose top-left image coordinate is (x0,y0) into shared memory with
-// row pitch tw.  Requirements for the bulk path (checked by the caller through `bulk_ok`: image base
-// 16-byte aligned and w % 16 == 0): tw % 16 == 0, x0 % 16 == 0, shared tile 16-byte aligned.  Rows
-// outside the image follow `mode` (REPLICATE / REFLECT101) by redirecting the source row; tiles that
-// stick out left or right take the ordinary-load path, which also handles those columns.  Ends with
-// the data visible to the whole block.
-__device__ __forceinline__ void stage_tile_bulk(uint8_t *sm, const uint8_t *__restrict__ img, int h, int w, int x0,
-                                                int y0, int tw, int th, int mode, bool bulk_ok, bool al,
+// row pitch tw.  Requirements for the bulk path (`bulk_ok`: image base 16-byte aligned and
+// pitch % 16 == 0 -- true for every plane the library allocates, whatever the image width):
+// tw % 16 == 0, x0 % 16 == 0, shared tile 16-byte aligned.  Rows outside the image follow `mode`
+// (REPLICATE / REFLECT101) by redirecting the source row; tiles that stick out left or right take
+// the ordinary-load path, which also handles those columns.  Ends with the data visible to the
+// whole block.
+__device__ __forceinline__ void stage_tile_bulk(uint8_t *sm, const uint8_t *__restrict__ img, int h, int w, int pitch,
+                                                int x0, int y0, int tw, int th, int mode, bool bulk_ok, bool al,
                                                 uint64_t *bar)
 {
     if (bulk_ok && x0 >= 0 && x0 + tw <= w) {            // block-uniform
@@ -63,12 +68,12 @@ __device__ __forceinline__ void stage_tile_bulk(uint8_t *sm, const uint8_t *__re
             if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, (uint32_t)(tw * th));
             for (int r = threadIdx.x; r < th; r += 32) {
                 int y = border_index(y0 + r, h, mode);
-                bulk_g2s(sm + r * tw, img + (size_t)y * w + x0, (uint32_t)tw, bar);
+                bulk_g2s(sm + r * tw, img + (size_t)y * pitch + x0, (uint32_t)tw, bar);
             }
         }
         mbar_wait(bar, 0);
     } else {
-        stage_tile_u8(sm, tw, img, h, w, x0, y0, tw, th, mode, al);
+        stage_tile_u8(sm, tw, img, h, w, pitch, x0, y0, tw, th, mode, al);
         __syncthreads();
     }
 }

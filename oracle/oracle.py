@@ -73,6 +73,14 @@ def contrast(rgb, factor):
     return out
 
 
+def enhance(rgb, contrast_factor=1.0, brightness_factor=1.0):
+    rgb, p = _u8(rgb)
+    h, w = rgb.shape[:2]
+    out = np.empty_like(rgb)
+    lib().o_enhance(p, h, w, C.c_double(contrast_factor), C.c_double(brightness_factor), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
 def _unary(fn, img, *args):
     img, p = _u8(img)
     h, w = img.shape[:2]

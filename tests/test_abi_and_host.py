@@ -44,7 +44,7 @@ def test_struct_layouts(built):
 def test_bad_arguments_fail_loudly(built):
     """Argument validation happens before any CUDA call, so it can be exercised without a GPU."""
     from img2sgf_b200 import _native as N
-    rc = N.lib().i2s_grey(None, None, 1, 10, 10, None)
+    rc = N.lib().i2s_grey(None, 0, None, 0, 1, 10, 10, None)
     assert rc == -1 and b"bad argument" in N.lib().i2s_last_error()
     with pytest.raises(N.NativeError):
         N.check(rc, "i2s_grey")
@@ -84,6 +84,44 @@ def test_shard_range():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_shard_by_pixels_and_groups():
+    from img2sgf_b200.batch import shard_by_pixels, group_by_size
+    rng = np.random.default_rng(0)
+    sizes = [(int(h), int(w)) for h, w in rng.integers(100, 1300, (40, 2))]
+    for world in (1, 2, 3, 8):
+        parts = shard_by_pixels(sizes, world)
+        assert sorted(i for p in parts for i in p) == list(range(40))
+        loads = [sum(sizes[i][0] * sizes[i][1] for i in p) for p in parts]
+        assert max(loads) - min(loads) <= max(h * w for h, w in sizes)        # LPT bound
+        assert parts == shard_by_pixels(sizes, world)                        # deterministic
+    groups = group_by_size(sizes, max_group=8)
+    assert sorted(i for g in groups for i in g) == list(range(40)) and max(len(g) for g in groups) <= 8
+    for g in groups:
+        ch, cw = max(sizes[i][0] for i in g), max(sizes[i][1] for i in g)
+        assert sum(sizes[i][0] * sizes[i][1] for i in g) >= 0.6 * ch * cw * len(g) or len(g) == 1
+    assert group_by_size([]) == [] and shard_by_pixels([], 2) == [[], []]
+
+
+def test_ragged_pack_layout():
+    """The packed layout RaggedRunner uploads: descriptors first, 16-byte aligned image starts,
+    4-byte aligned row pitches, pixels where the descriptors say."""
+    from img2sgf_b200.batch import RaggedRunner
+    from img2sgf_b200 import _native as N
+    rng = np.random.default_rng(1)
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in ((5, 7), (9, 3), (4, 10))]
+    nbytes, desc, ch, fill = RaggedRunner.pack(imgs, [2, 0, 1], thresholds=[11, 12, 13])
+    buf = np.zeros(nbytes, np.uint8)
+    fill(buf)
+    assert ch == 3 and desc.dtype == N.IMAGE_DTYPE and list(desc["line_threshold"]) == [13, 11, 12]
+    back = buf[:desc.nbytes].view(N.IMAGE_DTYPE)
+    assert (back == desc).all()
+    for k, i in enumerate([2, 0, 1]):
+        h, w = imgs[i].shape[:2]
+        o, p = int(desc[k]["offset"]), int(desc[k]["pitch"])
+        assert o % 16 == 0 and p % 4 == 0 and p >= 3 * w and (desc[k]["h"], desc[k]["w"]) == (h, w)
+        assert (buf[o:o + h * p].reshape(h, p)[:, :3 * w] == imgs[i].reshape(h, 3 * w)).all()
+
+
 def test_choose_threshold():
     from img2sgf_b200.api import choose_threshold
     assert choose_threshold(750, 747) == 74 and choose_threshold(110, 102) == 23
@@ -112,6 +150,18 @@ local = torch.zeros((e - s, RECORD_BYTES), dtype=torch.uint8)
 for i in range(s, e):
     local[i - s] = torch.from_numpy(np.random.default_rng(i).integers(0, 256, RECORD_BYTES, dtype=np.uint8))
 full = gather_records(local, total)
+# ragged batches: pixel-balanced assignment, records come back in input order on every rank
+from img2sgf_b200.batch import shard_by_pixels, gather_ragged_records
+from img2sgf_b200 import _native as N
+sizes = [(10 + 7 * i, 20 + 3 * i) for i in range(total)]
+assign = shard_by_pixels(sizes, world)
+mine = np.zeros(len(assign[rank]), N.RECORD_DTYPE)
+for k, i in enumerate(assign[rank]):
+    mine[k]["n_circles"] = 1000 + i
+    mine[k]["board"][:] = i % 3
+allrec = gather_ragged_records(mine, assign)
+assert list(allrec["n_circles"]) == [1000 + i for i in range(total)], allrec["n_circles"]
+assert all((allrec[i]["board"] == i % 3).all() for i in range(total))
 want = torch.stack([torch.from_numpy(np.random.default_rng(i).integers(0, 256, RECORD_BYTES, dtype=np.uint8))
                     for i in range(total)]) if total else torch.zeros((0, RECORD_BYTES), dtype=torch.uint8)
 assert full.shape == want.shape and bool((full == want).all()), (rank, full.shape)

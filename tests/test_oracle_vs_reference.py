@@ -58,6 +58,23 @@ def test_random_sparse_lines(seed, oracle):
         np.testing.assert_array_equal(np.asarray(ref_c, np.float64), oracle.cluster(got))
 
 
+@pytest.mark.parametrize("sliders", [(70, 50), (35, 80), (95, 20), (50, 50), (10, 100), (100, 0)])
+def test_enhance_vs_pil(sliders, oracle):
+    """ImageEnhance.Contrast / Brightness at several slider settings (img2sgf.py:142-149), incl. factors
+    inside [0,1] (PIL's interpolation branch) and far outside (its clipping branch)."""
+    from PIL import Image, ImageEnhance
+    cs, bs = sliders
+    fc, fb = 102 / (101 - cs) - 1, 450 / (200 - bs) - 2
+    rng = np.random.default_rng(cs * 1000 + bs)
+    for k in range(3):
+        h, w = int(rng.integers(5, 90)), int(rng.integers(5, 90))
+        rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        if k == 1:
+            rgb = (rgb // 3 + 160).astype(np.uint8)               # bright, low contrast
+        want = np.array(ImageEnhance.Brightness(ImageEnhance.Contrast(Image.fromarray(rgb)).enhance(fc)).enhance(fb))
+        np.testing.assert_array_equal(oracle.enhance(rgb, fc, fb), want)
+
+
 @pytest.mark.skipif(not __import__("os").path.exists("/root/reference/img2sgf.py"),
                     reason="the reference source exists in the build container only")
 def test_goldens_pinned_to_reference_source():
