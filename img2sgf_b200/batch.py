@@ -46,6 +46,9 @@ def shard_by_pixels(sizes, world: int) -> list[list[int]]:
     return [sorted(o) for o in out]
 
 
+RETRY_BITS = N.ST_CAND_OVERFLOW | N.ST_CIRCLE_OVERFLOW | N.ST_LINE_OVERFLOW | N.ST_HYST_NOT_CONVERGED
+
+
 def group_by_size(sizes, max_group: int = 32, max_waste: float = 0.35) -> list[list[int]]:
     """Groups of images that share one canvas (max h x max w of the group): images sorted by area,
     a group is closed when adding the next image would leave more than `max_waste` of the canvas
@@ -344,7 +347,29 @@ class RaggedRunner:
                        contrast_factor: float = 1.0, brightness_factor: float = 1.0) -> np.ndarray:
         """images: list of u8 arrays, [h,w,3] (RGB order) or [h,w] (greyscale sources), any sizes.
         Returns one record per image, in input order.  line_threshold None = choose_threshold() per image;
-        `thresholds` = optional per-image slider values."""
+        `thresholds` = optional per-image slider values.
+
+        Images whose status word reports an exceeded limit (candidates, circles, lines, hysteresis passes) are
+        re-run with enlarged limits, and the runner keeps the enlarged limits for later calls, so the
+        returned records are valid (status 0, or I2S_ST_GRID_OVERFLOW for a grid the record cannot hold)."""
+        from .api import _grow
+        kw = dict(line_threshold=line_threshold, black_threshold=black_threshold, contrast_factor=contrast_factor,
+                  brightness_factor=brightness_factor)
+        out = self._process(images, thresholds=thresholds, **kw)
+        for _ in range(8):
+            bad = np.nonzero(out["status"] & RETRY_BITS)[0]
+            if len(bad) == 0:
+                return out
+            lim = self.limits if self.limits is not None else N.default_limits()
+            self.limits = _grow(lim, int(np.bitwise_or.reduce(out["status"][bad]) & RETRY_BITS))
+            self._engines.clear()
+            torch.cuda.empty_cache()
+            sub_thr = [thresholds[i] for i in bad] if thresholds is not None else None
+            out[bad] = self._process([images[i] for i in bad], thresholds=sub_thr, **kw)
+        raise N.NativeError("retry budget exhausted: " + N.describe_status(int(out["status"].max())))
+
+    def _process(self, images, line_threshold=None, black_threshold: int = 128, thresholds=None,
+                 contrast_factor: float = 1.0, brightness_factor: float = 1.0) -> np.ndarray:
         total = len(images)
         out = np.zeros(total, N.RECORD_DTYPE)
         if total == 0:
@@ -438,9 +463,6 @@ def gather_ragged_records(local: np.ndarray, assignment: list[list[int]], group=
         out[idx] = allrec[r * per:r * per + len(idx)].reshape(-1).view(N.RECORD_DTYPE)
     assert len(assignment[rank]) == len(local)
     return out
-
-
-RETRY_BITS = N.ST_CAND_OVERFLOW | N.ST_CIRCLE_OVERFLOW | N.ST_LINE_OVERFLOW | N.ST_HYST_NOT_CONVERGED
 
 
 def failed_images(records_np: np.ndarray) -> np.ndarray:

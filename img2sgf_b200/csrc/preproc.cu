@@ -170,7 +170,7 @@ __device__ __forceinline__ uint32_t load_word_border(const uint8_t *__restrict__
     return v;
 }
 
-__global__ void __launch_bounds__(GR_WARPS * 32) k_gauss357_roll(const uint8_t *__restrict__ src, uint8_t *__restrict__ d3,
+__global__ void __launch_bounds__(GR_WARPS * 32, 4) k_gauss357_roll(const uint8_t *__restrict__ src, uint8_t *__restrict__ d3,
                                                                  uint8_t *__restrict__ d5, uint8_t *__restrict__ d7,
                                                                  const Dims dims, int spitch, size_t sstride, int pitch,
                                                                  size_t stride, int strips_x, int strips_y, int total)

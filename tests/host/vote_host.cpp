@@ -21,7 +21,8 @@ int cv_round(float v) { return (int)nearbyintf(v); }
 
 // img: h x w grey, edges: h x w (0/255, the Canny output the votes are cast from).
 // out_peaks: linear indices cy * (w + 2) + cx of the accumulator peaks, unsorted; returns their number,
-// or -1 if a vote ever left the shared tile (guard band too small) -- must never happen.
+// or -1 if a vote ever left the shared tile (guard band too small), -2 if the kernel's packed address
+// arithmetic disagrees with the plain one -- neither must ever happen.
 extern "C" int vh_vote_peaks(const uint8_t *img, const uint8_t *edges, int h, int w, float slack, int *out_peaks, int cap,
                              long long *votes_cast)
 {
@@ -74,6 +75,15 @@ extern "C" int vh_vote_peaks(const uint8_t *img, const uint8_t *edges, int h, in
                 for (int t = t_lo; t <= t_hi; t++, x1 += sx, y1 += sy) {
                     const int ly = y1 >> 10, lx = x1 >> 10;
                     if (ly < 0 || ly >= AS || lx < 0 || lx >= AS) return -1;
+                    {   // the kernel's packed form of the same cell (circles.cu, "The vote loop"): both offsets in one
+                        // register, U(t) = 0x80008000 + t * (sy * 65536 + sx); address by one 16-bit x 8-bit dot product
+                        const uint32_t S = (uint32_t)(sy * 65536 + sx);
+                        const uint32_t U = 0x80008000u + (uint32_t)t * S;
+                        const uint32_t m = (U >> 8) & 0x00FC00FCu;
+                        const uint32_t a0 = 4u * (uint32_t)((y - cy0 - 32) * AP + (x - cx0 - 32));
+                        const uint32_t addr = a0 + (m & 0xffffu) * 1u + (m >> 16) * (uint32_t)AP;
+                        if (addr != 4u * (uint32_t)(ly * AP + lx)) return -2;
+                    }
                     acc[ly * AP + lx]++;
                     cast++;
                 }
