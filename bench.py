@@ -449,14 +449,14 @@ def run_ours(args, rank, world, local_rank):
                    "images_per_s_all": total * args.steps / dtc,
                    "note": "the H2D copies of run_host alone (same pinned buffers, staging ring and copy streams, no kernels), "
                            "all ranks at once, slowest rank"}
-        if extras:
+        if not args.no_grey:
             # beside the RGB line: the diagrams ARE greyscale (R = G = B), so the single-plane entry gives the same records
             hostg = torch.from_numpy(grey).pin_memory()
             grunner = B.BatchRunner(size, size, chunk, streams=args.streams, channels=1, copy_streams=args.copy_streams)
-            rg = grunner.run_host(hostg, thr, 128)
+            rg = grunner.run_host(hostg, thr, 128, gather=gather)
             same = bool(rg.tobytes() == host_np.tobytes())
-            dtg = timed_host(lambda: grunner.run_host(hostg, thr, 128), args.steps)
-            e2e_grey = {"value": per_gpu * args.steps / dtg, "unit": UNIT, "h2d_bytes_per_step": int(per_gpu * size * size),
+            dtg = timed_host(lambda: grunner.run_host(hostg, thr, 128, gather=gather), args.steps)
+            e2e_grey = {"value": total * args.steps / dtg, "unit": UNIT, "h2d_bytes_per_step": int(per_gpu * size * size) * world,
                         "records_identical_to_rgb": same,
                         "note": "i2s_batch_t.channels = 1: exact for greyscale sources (8 of the reference's 17 test images "
                                 "are mode L); reported beside, not instead of, the RGB line"}
@@ -638,7 +638,8 @@ def main():
     ap.add_argument("--cpu-images", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the robustness / configs[2] / grey blocks (N=1)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the robustness / configs[2] blocks (N=1)")
+    ap.add_argument("--no-grey", action="store_true", help="skip the single-plane (greyscale source) end-to-end block")
     ap.add_argument("--images2048", type=int, default=512)
     ap.add_argument("--noisy-images", type=int, default=256)
     ap.add_argument("--fixture-images", type=int, default=2040)

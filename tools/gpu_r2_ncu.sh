@@ -4,7 +4,7 @@
 TAG=${TAG:-r2}
 mkdir -p gpurun_out; rm -f gpurun_out/*.ncu-rep
 python -c "import __graft_entry__ as g; g.build()" 2>&1 | tail -1
-ARGS="--no-cpu-baseline --no-e2e --no-extras"
+ARGS="--no-cpu-baseline --no-e2e --no-extras --no-grey"
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${TAG}_launches.csv \
    python bench.py --per-gpu 64 --steps 1 --warmup 1 --streams 1 $ARGS > gpurun_out/${TAG}_launches.log 2>&1; echo "launch list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on \
