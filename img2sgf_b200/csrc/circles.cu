@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(RW * 32) k_radius(const uint2 *__restrict__ ed
 {
     __shared__ int s_bins[RW][RBINS];
     __shared__ int s_pref[RW][RBINS];
-    __shared__ uint32_t s_mask[RW][RBINS / 32];
+    __shared__ short s_nzp[RW][RBINS];             // highest non-empty bin at or below b (-1: none)
     __shared__ float s_rtab[RQ];
     __shared__ uint16_t s_binlut[900];             // histogram bin of squared distance q + 0.5, q = 1..899
     const int map = blockIdx.y;
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(RW * 32) k_radius(const uint2 *__restrict__ ed
     }
     __syncthreads();
     int *bins = s_bins[warp], *pref = s_pref[warp];
-    uint32_t *mask = s_mask[warp];
+    short *nzp = s_nzp[warp];
     for (int c = blockIdx.x * RW + warp; c < n; c += gridDim.x * RW) {
         int base = cand[(size_t)map * cand_cap + c];
         int cy = base / aw, cx = base - cy * aw;
@@ -330,8 +330,18 @@ __global__ void __launch_bounds__(RW * 32) k_radius(const uint2 *__restrict__ ed
         // histogram of the distances to the edge pixels within 30 px: walk the edge-list buckets
         // that overlap the 60x60 window (at most 3x3 of them).  (A finer 16x16 directory was tried:
         // fewer entries to reject, but cells of ~18 entries leave half a warp idle -- slower.)
+        // Both differences travel in one register: (centre + 0x8000) - entry keeps the low half from
+        // borrowing, the xor turns it back into a signed 16-bit dx next to dy (|d| <= 92 inside 3x3
+        // buckets), and q = dx^2 + dy^2 + dx + dy is two 16-bit x 8-bit dot products.
         const int xlo = max(cx - 29, 0), xhi = min(cx + 30, w - 1);
         const int ylo = max(cy - 29, 0), yhi = min(cy + 30, h - 1);
+        const uint32_t cpk = (((uint32_t)cy << 16) | (uint32_t)cx) + 0x8000u;
+        auto tally = [&](uint32_t e) {
+            const int a = (int)((cpk - e) ^ 0x8000u);                        // (dy << 16) | (dx & 0xffff)
+            const int b = (int)__byte_perm((uint32_t)a, 0u, 0x4420);         // bytes (dx, dy)
+            const int q = __dp2a_lo(a, 0x0101, __dp2a_lo(a, b, 0));          // 1 <= r2 <= 900  <=>  1 <= q <= 899
+            if ((unsigned)(q - 1) < 899u) atomicAdd(bins + s_binlut[q], 1);
+        };
         for (int by = ylo / EB; by <= yhi / EB; by++)
             for (int bx = xlo / EB; bx <= xhi / EB; bx++) {
                 const int2 d = __ldg(mdir + by * nbx + bx);
@@ -340,37 +350,31 @@ __global__ void __launch_bounds__(RW * 32) k_radius(const uint2 *__restrict__ ed
                     const uint32_t e0 = __ldg(&elist[d.x + i].x);
                     const bool two = i + 32 < d.y;
                     const uint32_t e1 = two ? __ldg(&elist[d.x + i + 32].x) : 0u;
-                    {
-                        const int dxi = cx - (int)(e0 & 0xffff), dyi = cy - (int)(e0 >> 16);
-                        const int q = dxi * dxi + dxi + dyi * dyi + dyi;     // 1 <= r2 <= 900  <=>  1 <= q <= 899
-                        if ((unsigned)(q - 1) < 899u) atomicAdd(bins + s_binlut[q], 1);
-                    }
-                    if (two) {
-                        const int dxi = cx - (int)(e1 & 0xffff), dyi = cy - (int)(e1 >> 16);
-                        const int q = dxi * dxi + dxi + dyi * dyi + dyi;
-                        if ((unsigned)(q - 1) < 899u) atomicAdd(bins + s_binlut[q], 1);
-                    }
+                    tally(e0);
+                    if (two) tally(e1);
                 }
             }
         __syncwarp();
-        // inclusive prefix sums (10 bins per lane) and the non-zero bitmap
+        // inclusive prefix sums (10 bins per lane) and, per bin, the highest non-empty bin at or below it
         {
-            int loc[10], sum = 0;
+            int loc[10], sum = 0, top = -1;
 #pragma unroll
-            for (int k = 0; k < 10; k++) { loc[k] = bins[lane * 10 + k]; sum += loc[k]; }
-            int incl = sum;
+            for (int k = 0; k < 10; k++) { loc[k] = bins[lane * 10 + k]; sum += loc[k]; if (loc[k]) top = lane * 10 + k; }
+            int incl = sum, below = top;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
+                const int t = __shfl_up_sync(0xffffffffu, incl, o), u = __shfl_up_sync(0xffffffffu, below, o);
+                if (lane >= o) { incl += t; below = max(below, u); }
             }
+            below = __shfl_up_sync(0xffffffffu, below, 1);                   // over the lanes before this one
+            if (lane == 0) below = -1;
             int run = incl - sum;
 #pragma unroll
-            for (int k = 0; k < 10; k++) { run += loc[k]; pref[lane * 10 + k] = run; }
-#pragma unroll
-            for (int wd = 0; wd < RBINS / 32; wd++) {
-                uint32_t m = __ballot_sync(0xffffffffu, bins[wd * 32 + lane] != 0);
-                if (lane == 0) mask[wd] = m;
+            for (int k = 0; k < 10; k++) {
+                run += loc[k];
+                pref[lane * 10 + k] = run;
+                if (loc[k]) below = lane * 10 + k;
+                nzp[lane * 10 + k] = (short)below;
             }
         }
         __syncwarp();
@@ -380,11 +384,7 @@ __global__ void __launch_bounds__(RW * 32) k_radius(const uint2 *__restrict__ ed
         float rBest = 0.0f;
         int j = NBINS - 1;
         while (j > 0) {
-            int wd = j >> 5;
-            uint32_t m = mask[wd] & (0xffffffffu >> (31 - (j & 31)));
-            while (m == 0 && --wd >= 0) m = mask[wd];
-            if (m == 0) break;
-            int up = wd * 32 + 31 - __clz(m);
+            const int up = nzp[j];
             if (up <= 0) break;
             int jn = up - 10, cur;
             if (jn >= 0) cur = pref[up] - pref[jn];
@@ -426,17 +426,18 @@ struct FinishBufs {
     uint8_t *state;                  // np2cap   0 undecided, 1 kept, 2 rejected
 };
 constexpr int FINISH_SMEM_CAP = 8192;
+constexpr int FINISH_THREADS = 1024;         // a map with thousands of candidates (the edge-map input) sets the launch's critical path
 constexpr int FINISH_MAX_CELLS = 4096;
 __host__ __device__ static inline size_t finish_bytes_per_map(int np2cap) { return (size_t)np2cap * 16; }
 
-__global__ void __launch_bounds__(256) k_circles_finish(const unsigned long long *__restrict__ est,
+__global__ void __launch_bounds__(FINISH_THREADS) k_circles_finish(const unsigned long long *__restrict__ est,
                                                         const int32_t *__restrict__ nest, int cand_cap, int np2cap,
                                                         int cshift, int cells_x, int cells_y, float *circ,
                                                         int32_t *ncirc, int circle_cap, int32_t *status, int n_images,
                                                         unsigned char *gbuf)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    __shared__ int s_flag, s_warp_tot[8];
+    __shared__ int s_flag, s_warp_tot[FINISH_THREADS / 32];
     const int map = blockIdx.x;
     int *head = reinterpret_cast<int *>(s_raw);                                            // cells_x * cells_y
     unsigned char *arr = gbuf ? gbuf + (size_t)map * finish_bytes_per_map(np2cap)
@@ -513,7 +514,7 @@ __global__ void __launch_bounds__(256) k_circles_finish(const unsigned long long
     if (lane == 31) s_warp_tot[warp] = incl;
     __syncthreads();
     int before = incl - mine, nk = 0;
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < FINISH_THREADS / 32; k++) {
         if (k < warp) before += s_warp_tot[k];
         nk += s_warp_tot[k];
     }
@@ -738,7 +739,7 @@ int hough_circles_maps(const MapSet &ms, const Dims &dims, float *mcirc, int32_t
     const int cells_x = (w >> cshift) + 1, cells_y = (h >> cshift) + 1;
     size_t smem = (((size_t)cells_x * cells_y * 4 + 15) & ~(size_t)15) + (gbuf ? 0 : finish_bytes_per_map(np2));
     I2S_CUDA(cudaFuncSetAttribute(k_circles_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_circles_finish<<<maps, 256, smem, st>>>(est, nest, lim.cand_cap, np2, cshift, cells_x, cells_y, mcirc, mcount,
+    k_circles_finish<<<maps, FINISH_THREADS, smem, st>>>(est, nest, lim.cand_cap, np2, cshift, cells_x, cells_y, mcirc, mcount,
                                               lim.circle_cap, status, ms.n, gbuf);
     I2S_CHECK_LAUNCH("k_circles_finish");
     return I2S_OK;

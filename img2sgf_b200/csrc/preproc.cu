@@ -10,6 +10,7 @@
 #include "profile.cuh"
 #include "tma.cuh"
 #include "roll_cores.cuh"
+#include "median_cores.cuh"
 
 namespace i2s {
 
@@ -251,18 +252,17 @@ int gauss357(const uint8_t *src, int spitch, size_t sstride, uint8_t *d3, uint8_
 // a stride of b+3 bits) and selects the median MSB-first: with C the set of still-possible window
 // elements and k the rank wanted inside C, the next result bit is 0 iff k < popc(C & ~plane), which
 // also narrows C.  No sorting network, no histogram.
-constexpr int MT_W = 64, MT_H = 32;
 
 // Median of the B x B windows of 4 adjacent pixels (row ty, columns gx..gx+3 of the tile) from the bit
 // planes of a tile staged with a halo of RS rows / HX columns.  Warp-uniform control flow (one
 // __any_sync): call it with all 32 lanes.  Returns the 4 result bytes.
 template <int B, int RS, int HX, int SH, int GW>
-__device__ __forceinline__ uint32_t median4_planes(const uint32_t (&s_bits)[10][SH][GW + 1], int ty, int gx, bool live)
+__device__ __forceinline__ uint32_t median4_planes(const uint32_t (&s_bits)[10][SH][GW + 1],
+                                                   const uint32_t (&s_set)[3][2][MT_H][MT_W / 32], int ty, int gx, bool live)
 {
     constexpr int F = B + 3;                         // window columns of 4 adjacent pixels
     constexpr int RPW = 32 / F;                      // window rows packed per 32-bit word
     constexpr int NW = (B + RPW - 1) / RPW;          // words per window
-    constexpr int KM = (B * B) / 2 + 1;              // a value held by KM window pixels is the median
     constexpr int RO = RS - B / 2;                   // first window row inside the staged halo
     // per-word masks of the B low bits of every packed row field
     uint32_t fm[NW];
@@ -284,26 +284,14 @@ __device__ __forceinline__ uint32_t median4_planes(const uint32_t (&s_bits)[10][
             P[r / RPW] |= bits << ((r % RPW) * F);
         }
     };
-    // Shortcut (exact): if at least KM of the B*B window pixels equal 255 the median is 255, likewise
-    // for 0.  Printed diagrams are mostly saturated paper and ink, so most warps finish here.
-    uint32_t packed = 0;
-    bool open = false;                               // some pixel of this thread still needs the selection
-    {
-        uint32_t P255[NW], P0[NW];
-        gather(8, P255);
-        gather(9, P0);
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            int c255 = 0, c0 = 0;
-#pragma unroll
-            for (int wd = 0; wd < NW; wd++) {
-                c255 += __popc((P255[wd] >> j) & fm[wd]);
-                c0 += __popc((P0[wd] >> j) & fm[wd]);
-            }
-            if (c255 >= KM) packed |= 0xffu << (8 * j);
-            else if (c0 < KM) open = true;
-        }
-    }
+    // Shortcut (exact): if more than half of the B*B window pixels equal 255 the median is 255, likewise
+    // for 0.  Printed diagrams are mostly saturated paper and ink, so most warps finish here.  The
+    // verdicts come from median_settle() as one bit per pixel.
+    constexpr int BI = B / 2 - 1;
+    const uint32_t m255 = (s_set[BI][0][ty][gx >> 5] >> (gx & 31)) & 0xfu;
+    const uint32_t m0 = (s_set[BI][1][ty][gx >> 5] >> (gx & 31)) & 0xfu;
+    uint32_t packed = ((m255 * 0x00204081u) & 0x01010101u) * 0xffu;      // 0xff in the bytes of the settled-255 pixels
+    const bool open = (m255 | m0) != 0xfu;           // some pixel of this thread still needs the selection
     if (__any_sync(0xffffffffu, open && live)) {
         uint32_t P[8][NW];
 #pragma unroll
@@ -338,6 +326,22 @@ __device__ __forceinline__ uint32_t median4_planes(const uint32_t (&s_bits)[10][
     return packed;
 }
 
+template <int MASK, int RS, int HX, int SH, int GW>
+__device__ __forceinline__ void median_settle(const uint32_t (&s_bits)[10][SH][GW + 1], uint32_t (&s_set)[3][2][MT_H][MT_W / 32])
+{
+    constexpr int WORDS = MT_W / 32, UNITS = 3 * MT_H * WORDS;
+    for (int u = threadIdx.x; u < UNITS; u += blockDim.x) {
+        const int bi = u / (MT_H * WORDS), rest = u - bi * (MT_H * WORDS), ty = rest / WORDS, j = rest - ty * WORDS;
+        if (!((MASK >> bi) & 1)) continue;
+        uint32_t a, b;
+        if (bi == 0) { a = settle_word<3, RS, HX, SH, GW>(s_bits[8], ty, j); b = settle_word<3, RS, HX, SH, GW>(s_bits[9], ty, j); }
+        else if (bi == 1) { a = settle_word<5, RS, HX, SH, GW>(s_bits[8], ty, j); b = settle_word<5, RS, HX, SH, GW>(s_bits[9], ty, j); }
+        else { a = settle_word<7, RS, HX, SH, GW>(s_bits[8], ty, j); b = settle_word<7, RS, HX, SH, GW>(s_bits[9], ty, j); }
+        s_set[bi][0][ty][j] = a;
+        s_set[bi][1][ty][j] = b;
+    }
+}
+
 // MASK selects the window sizes computed from ONE staged tile and ONE set of bit planes:
 // bit 0 -> 3x3 into dst3, bit 1 -> 5x5 into dst5, bit 2 -> 7x7 into dst7.
 template <int MASK> __global__ void __launch_bounds__(256, 4) k_median(const uint8_t *__restrict__ src,
@@ -350,6 +354,7 @@ template <int MASK> __global__ void __launch_bounds__(256, 4) k_median(const uin
     constexpr int GW = (SW + 31) / 32;               // 32-pixel groups per tile row
     __shared__ __align__(128) uint8_t s_in[SH * SW];
     __shared__ uint32_t s_bits[10][SH][GW + 1];      // planes 0..7: bits of the pixel; 8: pixel == 255; 9: pixel == 0
+    __shared__ uint32_t s_set[3][2][MT_H][MT_W / 32]; // per window size: median settled at 255 / at 0, one bit per pixel
     __shared__ uint64_t s_bar;
     const int2 wh = dims.of(blockIdx.z);
     const int w = wh.x, h = wh.y;
@@ -383,6 +388,8 @@ template <int MASK> __global__ void __launch_bounds__(256, 4) k_median(const uin
         for (int i = threadIdx.x; i < 10 * SH; i += blockDim.x) s_bits[i / SH][i % SH][GW] = 0;   // pad word
     }
     __syncthreads();
+    median_settle<MASK, RS, HX, SH, GW>(s_bits, s_set);
+    __syncthreads();
     // A warp covers a compact 16 x 8 pixel patch (lane = 4-pixel group lane%4 of row lane/4), so that
     // the saturated-window shortcut applies to whole warps as often as possible.
     for (int q = warp; q < (MT_W / 16) * (MT_H / 8); q += 8) {
@@ -390,9 +397,9 @@ template <int MASK> __global__ void __launch_bounds__(256, 4) k_median(const uin
         const int y = y0 + ty, x = x0 + gx;
         const bool live = y < h && x < w;
         const size_t o = blockIdx.z * stride + (size_t)y * pitch;
-        if (MASK & 4) { const uint32_t v = median4_planes<7, RS, HX, SH, GW>(s_bits, ty, gx, live); if (live) store4(dst7 + o, x, w, wlim, al, v); }
-        if (MASK & 2) { const uint32_t v = median4_planes<5, RS, HX, SH, GW>(s_bits, ty, gx, live); if (live) store4(dst5 + o, x, w, wlim, al, v); }
-        if (MASK & 1) { const uint32_t v = median4_planes<3, RS, HX, SH, GW>(s_bits, ty, gx, live); if (live) store4(dst3 + o, x, w, wlim, al, v); }
+        if (MASK & 4) { const uint32_t v = median4_planes<7, RS, HX, SH, GW>(s_bits, s_set, ty, gx, live); if (live) store4(dst7 + o, x, w, wlim, al, v); }
+        if (MASK & 2) { const uint32_t v = median4_planes<5, RS, HX, SH, GW>(s_bits, s_set, ty, gx, live); if (live) store4(dst5 + o, x, w, wlim, al, v); }
+        if (MASK & 1) { const uint32_t v = median4_planes<3, RS, HX, SH, GW>(s_bits, s_set, ty, gx, live); if (live) store4(dst3 + o, x, w, wlim, al, v); }
     }
 }
 
