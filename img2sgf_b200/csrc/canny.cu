@@ -312,11 +312,30 @@ __device__ __forceinline__ void hyst_tile(uint8_t *__restrict__ state, int spitc
     }
 }
 
-// Every pass walks the dirty flags with a grid sized for the machine, not for the tile count: a pass over
-// mostly clean maps -- the usual case after the first pass, and in the first pass too for crisp diagrams --
-// is one small launch whose blocks read a few dozen flags each (hyst_tile returns at once for a clean tile).
-__global__ void __launch_bounds__(256) k_hysteresis_pass(uint8_t *__restrict__ state, int spitch, size_t sstride,
-                                                         const Dims dims, int n_images, int tiles_x, int tiles_y, int tiles,
+// Every pass compacts the indices of the dirty tiles (k_hyst_list) and walks that list with a grid
+// sized for the machine, not for the tile count (k_hysteresis_list): a pass over mostly clean maps
+// -- the usual case after the first pass, and in the first pass too for crisp diagrams -- costs two
+// small launches instead of one block per tile.  (One launch per pass whose blocks walk the flags
+// themselves was measured slower: every clean tile then costs a block-wide barrier.)
+__global__ void __launch_bounds__(256) k_hyst_list(const uint8_t *__restrict__ dirty, int tiles, int *__restrict__ list,
+                                                   int *count)
+{
+    const int lane = threadIdx.x & 31;
+    for (int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31; base < tiles; base += gridDim.x * blockDim.x) {
+        const int t = base + lane;
+        const bool d = t < tiles && dirty[t];
+        const uint32_t m = __ballot_sync(0xffffffffu, d);
+        if (m == 0) continue;
+        int at = 0;
+        if (lane == 0) at = atomicAdd(count, __popc(m));
+        at = __shfl_sync(0xffffffffu, at, 0);
+        if (d) list[at + __popc(m & ((1u << lane) - 1u))] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_hysteresis_list(uint8_t *__restrict__ state, int spitch, size_t sstride,
+                                                         const Dims dims, int n_images, int tiles_x, int tiles_y,
+                                                         const int *__restrict__ list, const int *__restrict__ count,
                                                          uint8_t *dirty_in, uint8_t *dirty_out)
 {
     extern __shared__ __align__(16) uint8_t s_dyn[];
@@ -324,12 +343,14 @@ __global__ void __launch_bounds__(256) k_hysteresis_pass(uint8_t *__restrict__ s
     uint16_t *s_q = reinterpret_cast<uint16_t *>(s_dyn + HS_H * HS_W);
     __shared__ int s_qn, s_changed, s_ring;
     __shared__ uint64_t s_bar;
+    const int n = *count;
+    if ((int)blockIdx.x >= n) return;
     if (threadIdx.x == 0) mbar_init(&s_bar, 1);
     __syncthreads();
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-        hyst_tile(state, spitch, sstride, dims, n_images, tiles_x, tiles_y, dirty_in, dirty_out, t, s_map, s_q, s_qn, s_changed,
-                  s_ring, s_bar, phase);
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        hyst_tile(state, spitch, sstride, dims, n_images, tiles_x, tiles_y, dirty_in, dirty_out, list[i], s_map, s_q, s_qn,
+                  s_changed, s_ring, s_bar, phase);
         __syncthreads();                                   // shared state is reused by the next tile ...
         fence_proxy_async();                               // ... whose bulk copies must not overtake this tile's accesses
     }
@@ -363,10 +384,13 @@ __global__ void __launch_bounds__(256) k_state_to_edges16(const uint4 *__restric
     }
 }
 
+constexpr int HYST_RING = 64;                     // size of the per-pass list-counter ring, not a limit on passes
+
 size_t canny_scratch_bytes(int maps, int h, int w)
 {
     size_t tiles = (size_t)maps * cdiv(w, HT) * cdiv(h, HT);
-    return align_up(tiles, 256) * 2 + 256;                 // two dirty-flag buffers
+    // two dirty-flag buffers, the dirty-tile list, one list counter per pass
+    return align_up(tiles, 256) * 2 + align_up(tiles * sizeof(int), 256) + HYST_RING * sizeof(int) + 256;
 }
 
 // state: [ms.count * ms.n] planes of `spitch` bytes per row, `sstride` bytes apart; map m = k * ms.n + i
@@ -412,12 +436,20 @@ int hysteresis(uint8_t *state, int spitch, size_t sstride, const Dims &dims, int
     uint8_t *d0 = (uint8_t *)scratch, *d1 = d0 + align_up(tiles, 256);
     if (passes < 1) passes = 1;
     constexpr int kSmem = HS_H * HS_W + HQ * 2;
-    I2S_CUDA(cudaFuncSetAttribute(k_hysteresis_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    const unsigned grid = (unsigned)min((size_t)(4 * sm_count()), tiles);
+    I2S_CUDA(cudaFuncSetAttribute(k_hysteresis_list, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    int *list = (int *)(d1 + align_up(tiles, 256));
+    int *counts = (int *)((uint8_t *)list + align_up(tiles * sizeof(int), 256));
+    I2S_CUDA(cudaMemsetAsync(counts, 0, HYST_RING * sizeof(int), st));
+    const int sms = sm_count();
     for (int p = 0; p < passes; p++) {
         uint8_t *din = (p & 1) ? d1 : d0, *dout = (p & 1) ? d0 : d1;
-        k_hysteresis_pass<<<grid, 256, kSmem, st>>>(state, spitch, sstride, dims, n_images, tx, ty, (int)tiles, din, dout);
-        I2S_CHECK_LAUNCH("k_hysteresis_pass");
+        int *cnt = counts + p % HYST_RING;                     // the counters are a ring: re-zero a slot before reuse
+        if (p >= HYST_RING) I2S_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int), st));
+        k_hyst_list<<<(unsigned)min((size_t)(4 * sms), (tiles + 255) / 256), 256, 0, st>>>(din, (int)tiles, list, cnt);
+        I2S_CHECK_LAUNCH("k_hyst_list");
+        k_hysteresis_list<<<(unsigned)min((size_t)(4 * sms), tiles), 256, kSmem, st>>>(state, spitch, sstride, dims, n_images, tx,
+                                                                                        ty, list, cnt, din, dout);
+        I2S_CHECK_LAUNCH("k_hysteresis_list");
     }
     uint8_t *last = (passes & 1) ? d1 : d0;   // buffer written by the final pass
     k_hyst_check<<<maps, 128, 0, st>>>(last, tx * ty, n_images, status);

@@ -286,7 +286,7 @@ constexpr int RW = 8;          // warps per block
 constexpr int RBINS = 320;     // NBINS padded to a multiple of 32 (pad stays zero)
 constexpr int RQ = 576;        // radius table size: q = upbin + j <= 289 + 279
 
-__global__ void __launch_bounds__(RW * 32) k_radius(const uint2 *__restrict__ edges, size_t estride,
+__global__ void __launch_bounds__(RW * 32, 6) k_radius(const uint2 *__restrict__ edges, size_t estride,
                                                    const int2 *__restrict__ dir, int nbx, int nby, const Dims dims,
                                                    int n_images, const int32_t *__restrict__ cand,
                                                    const int32_t *__restrict__ ncand, int cand_cap, unsigned long long *est,

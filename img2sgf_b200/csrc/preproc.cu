@@ -356,6 +356,7 @@ template <int MASK> __global__ void __launch_bounds__(256, 4) k_median(const uin
     __shared__ uint32_t s_bits[10][SH][GW + 1];      // planes 0..7: bits of the pixel; 8: pixel == 255; 9: pixel == 0
     __shared__ uint32_t s_set[3][2][MT_H][MT_W / 32]; // per window size: median settled at 255 / at 0, one bit per pixel
     __shared__ uint64_t s_bar;
+    __shared__ int s_next;                           // next (window size, patch) item to hand out
     const int2 wh = dims.of(blockIdx.z);
     const int w = wh.x, h = wh.y;
     const int x0 = blockIdx.x * MT_W, y0 = blockIdx.y * MT_H;
@@ -367,6 +368,7 @@ template <int MASK> __global__ void __launch_bounds__(256, 4) k_median(const uin
     const bool al = ((reinterpret_cast<uintptr_t>(dst3) | reinterpret_cast<uintptr_t>(dst5) | reinterpret_cast<uintptr_t>(dst7) |
                       (uintptr_t)pitch | (uintptr_t)stride) & 3) == 0;
     const int wlim = write_limit(w, pitch, 4);
+    if (threadIdx.x == 0) s_next = 0;
     stage_tile_bulk(s_in, img, h, w, spitch, x0 - HX, y0 - RS, SW, SH, BORDER_REPLICATE, bulk, al_in, &s_bar);
     {   // bit planes: s_bits[b][row][g] bit i = bit b of tile pixel (row, 32 g + i).  A thread turns
         // 8 adjacent pixels into one byte of every plane: bit b of the 4 bytes of a word is gathered
@@ -391,15 +393,25 @@ template <int MASK> __global__ void __launch_bounds__(256, 4) k_median(const uin
     median_settle<MASK, RS, HX, SH, GW>(s_bits, s_set);
     __syncthreads();
     // A warp covers a compact 16 x 8 pixel patch (lane = 4-pixel group lane%4 of row lane/4), so that
-    // the saturated-window shortcut applies to whole warps as often as possible.
-    for (int q = warp; q < (MT_W / 16) * (MT_H / 8); q += 8) {
+    // the saturated-window shortcut applies to whole warps as often as possible.  A patch costs ~100
+    // instructions when the shortcut settles it and ~2500 when it does not, so the (window size, patch)
+    // items are handed out dynamically, largest windows first: warps that finish early take more.
+    constexpr int PATCHES = (MT_W / 16) * (MT_H / 8);
+    constexpr int NSIZES = ((MASK >> 2) & 1) + ((MASK >> 1) & 1) + (MASK & 1);
+    while (true) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(&s_next, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= NSIZES * PATCHES) break;
+        const int q = item % PATCHES;
+        int which = item / PATCHES;                  // index among the enabled sizes, 7 first
         const int ty = (q / (MT_W / 16)) * 8 + (lane >> 2), gx = ((q % (MT_W / 16)) * 4 + (lane & 3)) * 4;
         const int y = y0 + ty, x = x0 + gx;
         const bool live = y < h && x < w;
         const size_t o = blockIdx.z * stride + (size_t)y * pitch;
-        if (MASK & 4) { const uint32_t v = median4_planes<7, RS, HX, SH, GW>(s_bits, s_set, ty, gx, live); if (live) store4(dst7 + o, x, w, wlim, al, v); }
-        if (MASK & 2) { const uint32_t v = median4_planes<5, RS, HX, SH, GW>(s_bits, s_set, ty, gx, live); if (live) store4(dst5 + o, x, w, wlim, al, v); }
-        if (MASK & 1) { const uint32_t v = median4_planes<3, RS, HX, SH, GW>(s_bits, s_set, ty, gx, live); if (live) store4(dst3 + o, x, w, wlim, al, v); }
+        if (MASK & 4) { if (which == 0) { const uint32_t v = median4_planes<7, RS, HX, SH, GW>(s_bits, s_set, ty, gx, live); if (live) store4(dst7 + o, x, w, wlim, al, v); } which--; }
+        if (MASK & 2) { if (which == 0) { const uint32_t v = median4_planes<5, RS, HX, SH, GW>(s_bits, s_set, ty, gx, live); if (live) store4(dst5 + o, x, w, wlim, al, v); } which--; }
+        if (MASK & 1) { if (which == 0) { const uint32_t v = median4_planes<3, RS, HX, SH, GW>(s_bits, s_set, ty, gx, live); if (live) store4(dst3 + o, x, w, wlim, al, v); } which--; }
     }
 }
 
