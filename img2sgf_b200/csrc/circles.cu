@@ -136,6 +136,14 @@ constexpr int VOTE_SMEM = AS * AP * 4;
 constexpr int VB = 7;                        // buckets per axis that can overlap a tile's region
 static_assert(AP < 256, "the pitch is a byte operand of the address dot product");
 
+// 1/v for |v| >= 1 (a non-zero Q10 step): the bare MUFU.RCP, 1 ulp -- the clip interval has 0.25 of slack
+__device__ __forceinline__ float rcp_approx(float v)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
 __device__ __forceinline__ void vote_at(uint32_t a0, uint32_t U)
 {
     const uint32_t m = (U >> 8) & 0x00FC00FCu;
@@ -149,12 +157,12 @@ __device__ __forceinline__ void vote_item(int *s_acc, uint32_t s_base, uint2 e, 
     const int sx = (int)(short)(e.y & 0xffff), sy = (int)e.y >> 16;
     float lo = -(float)MAX_R, hi = (float)MAX_R;
     if (sx != 0) {
-        float inv = __fdividef(1024.0f, (float)sx);
+        float inv = 1024.0f * rcp_approx((float)sx);
         float ta = (float)(X0 - x) * inv, tb = (float)(X1 + 1 - x) * inv;
         lo = fmaxf(lo, fminf(ta, tb)); hi = fminf(hi, fmaxf(ta, tb));
     } else if (x < X0 || x > X1) return;
     if (sy != 0) {
-        float inv = __fdividef(1024.0f, (float)sy);
+        float inv = 1024.0f * rcp_approx((float)sy);
         float ta = (float)(Y0 - y) * inv, tb = (float)(Y1 + 1 - y) * inv;
         lo = fmaxf(lo, fminf(ta, tb)); hi = fminf(hi, fmaxf(ta, tb));
     } else if (y < Y0 || y > Y1) return;
@@ -417,13 +425,13 @@ __global__ void __launch_bounds__(RW * 32, 6) k_radius(const uint2 *__restrict__
 // is the sequential algorithm's by induction over the sorted order -- a handful of rounds instead of
 // one dependent step per candidate.  The kept circles are compacted in sorted order by a block scan.
 //
-// Working arrays (15 bytes per candidate) live in shared memory up to 8192 candidates per map and in
+// Working arrays (16 bytes per candidate) live in shared memory up to 8192 candidates per map and in
 // the caller's workspace above that, so any cand_cap the limits accept runs.
 struct FinishBufs {
     unsigned long long *keys;        // np2cap
     short2 *xy;                      // np2cap
     uint16_t *next;                  // np2cap
-    uint8_t *state;                  // np2cap   0 undecided, 1 kept, 2 rejected
+    uint8_t *state;                  // 2 x np2cap   0 undecided, 1 kept, 2 rejected (two copies, see the rounds)
 };
 constexpr int FINISH_SMEM_CAP = 8192;
 constexpr int FINISH_THREADS = 1024;         // a map with thousands of candidates (the edge-map input) sets the launch's critical path
@@ -437,7 +445,7 @@ __global__ void __launch_bounds__(FINISH_THREADS) k_circles_finish(const unsigne
                                                         unsigned char *gbuf)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    __shared__ int s_flag, s_warp_tot[FINISH_THREADS / 32];
+    __shared__ int s_warp_tot[FINISH_THREADS / 32];
     const int map = blockIdx.x;
     int *head = reinterpret_cast<int *>(s_raw);                                            // cells_x * cells_y
     unsigned char *arr = gbuf ? gbuf + (size_t)map * finish_bytes_per_map(np2cap)
@@ -463,42 +471,44 @@ __global__ void __launch_bounds__(FINISH_THREADS) k_circles_finish(const unsigne
         const int prev = atomicExch(&head[(y >> cshift) * cells_x + (x >> cshift)], i);
         B.next[i] = (uint16_t)(prev < 0 ? 0xffff : prev);
     }
-    volatile uint8_t *vstate = B.state;
+    // Rounds on two copies of the state: decisions are taken from the previous round's copy and written to the
+    // other one, so no thread ever reads a byte another thread may be writing.
+    uint8_t *cur = B.state, *nxt = B.state + np2cap;
+    __syncthreads();
     while (true) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_flag = 0;
-        __syncthreads();
         bool waiting = false;
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            if (vstate[i]) continue;
-            const short2 p = B.xy[i];
-            const int ccx = p.x >> cshift, ccy = p.y >> cshift;
-            bool any_kept = false, all_rejected = true;
-            for (int dy = -1; dy <= 1; dy++) {
-                const int ny = ccy + dy;
-                if (ny < 0 || ny >= cells_y) continue;
-                for (int dx = -1; dx <= 1; dx++) {
-                    const int nx = ccx + dx;
-                    if (nx < 0 || nx >= cells_x) continue;
-                    for (int j = head[ny * cells_x + nx]; j >= 0; j = (B.next[j] == 0xffff) ? -1 : (int)B.next[j]) {
-                        if (j >= i) continue;
-                        const short2 q = B.xy[j];
-                        const int ex = q.x - p.x, ey = q.y - p.y;
-                        if (ex * ex + ey * ey >= 100) continue;
-                        const int s = vstate[j];
-                        any_kept |= s == 1;
-                        all_rejected &= s == 2;
+            uint8_t s = cur[i];
+            if (!s) {
+                const short2 p = B.xy[i];
+                const int ccx = p.x >> cshift, ccy = p.y >> cshift;
+                bool any_kept = false, all_rejected = true;
+                for (int dy = -1; dy <= 1; dy++) {
+                    const int ny = ccy + dy;
+                    if (ny < 0 || ny >= cells_y) continue;
+                    for (int dx = -1; dx <= 1; dx++) {
+                        const int nx = ccx + dx;
+                        if (nx < 0 || nx >= cells_x) continue;
+                        for (int j = head[ny * cells_x + nx]; j >= 0; j = (B.next[j] == 0xffff) ? -1 : (int)B.next[j]) {
+                            if (j >= i) continue;
+                            const short2 q = B.xy[j];
+                            const int ex = q.x - p.x, ey = q.y - p.y;
+                            if (ex * ex + ey * ey >= 100) continue;
+                            const int sj = cur[j];
+                            any_kept |= sj == 1;
+                            all_rejected &= sj == 2;
+                        }
                     }
                 }
+                s = any_kept ? 2 : (all_rejected ? 1 : 0);
+                waiting |= s == 0;
             }
-            if (any_kept) vstate[i] = 2;
-            else if (all_rejected) vstate[i] = 1;
-            else waiting = true;
+            nxt[i] = s;
         }
-        if (waiting) s_flag = 1;
-        __syncthreads();
-        if (!s_flag) break;
+        uint8_t *t = cur; cur = nxt; nxt = t;
+        if (!__syncthreads_or(waiting)) break;
     }
+    B.state = cur;
     // kept circles in sorted order: contiguous slice per thread, block scan of the kept counts
     const int per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
     const int i0 = min((int)threadIdx.x * per, n), i1 = min(i0 + per, n);

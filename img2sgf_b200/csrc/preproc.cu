@@ -299,9 +299,9 @@ __device__ __forceinline__ uint32_t median4_planes(const uint32_t (&s_bits)[10][
         packed = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            uint32_t C[NW];
+            uint32_t C[NW];                          // candidate set, kept shifted to pixel j's window columns
 #pragma unroll
-            for (int wd = 0; wd < NW; wd++) C[wd] = fm[wd];
+            for (int wd = 0; wd < NW; wd++) C[wd] = fm[wd] << j;
             int k = (B * B) / 2;
             uint32_t val = 0;
 #pragma unroll
@@ -310,7 +310,7 @@ __device__ __forceinline__ uint32_t median4_planes(const uint32_t (&s_bits)[10][
                 int nz = 0;
 #pragma unroll
                 for (int wd = 0; wd < NW; wd++) {
-                    uint32_t pj = P[bit][wd] >> j;
+                    const uint32_t pj = P[bit][wd];
                     Z[wd] = C[wd] & ~pj;
                     O[wd] = C[wd] & pj;
                     nz += __popc(Z[wd]);
