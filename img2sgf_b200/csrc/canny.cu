@@ -81,11 +81,14 @@ __device__ __forceinline__ uint32_t grey4_from_rgb(uint32_t r0, uint32_t r1, uin
 
 template <int CH, int MINB>
 __global__ void __launch_bounds__(CR_WARPS * 32, MINB) k_canny_roll(const MapSet ms, const Dims dims, uint8_t *__restrict__ state,
-                                                              int spitch, size_t sstride, uint32_t low1, uint32_t high1,
+                                                              int spitch, size_t sstride, roll::h2 low, roll::h2 high,
                                                               int strips_x, int strips_y, int total,
                                                               uint8_t *__restrict__ tile_weak, int tiles_x,
                                                               uint8_t *__restrict__ grey, int gpitch, size_t gstride)
 {
+    __shared__ uint16_t s_tab[roll::SECTOR_TABLE];             // sector boundary per |dx| (roll_cores.cuh)
+    for (int i = threadIdx.x; i < roll::SECTOR_TABLE; i += blockDim.x) s_tab[i] = roll::sector_table_entry(i);
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int strip = blockIdx.x * CR_WARPS + (threadIdx.x >> 5);
     if (strip >= total) return;                                // warp-uniform
@@ -143,7 +146,8 @@ __global__ void __launch_bounds__(CR_WARPS * 32, MINB) k_canny_roll(const MapSet
                 if (it >= 2) {                                 // gradient + magnitude of row gy = py - 1
                     const int gy = py - 1;
                     roll::Grad g = roll::sobel_grad(R[(u + 1) % 3][0], R[(u + 2) % 3][0], R[u % 3][0]);
-                    uint32_t mA = g.axA + g.ayA, mB = g.axB + g.ayB;
+                    roll::h2 mA, mB;
+                    roll::grad_mag(g, mA, mB);
 #pragma unroll
                     for (int c = 1; c < CH; c++) {
                         const roll::Grad gc = roll::sobel_grad(R[(u + 1) % 3][c], R[(u + 2) % 3][c], R[u % 3][c]);
@@ -164,10 +168,10 @@ __global__ void __launch_bounds__(CR_WARPS * 32, MINB) k_canny_roll(const MapSet
                     // rows without a single magnitude above `low` in the whole warp (blank paper, and most
                     // of a median-filtered map, whose thin grid lines are gone) skip the NMS arithmetic
                     uint32_t st = 0;
-                    if (__any_sync(0xffffffffu, roll::any_above(c, low1))) {
-                        roll::NmsPartial p = roll::nms_axis(up, c, dn, g, low1);
-                        if (__any_sync(0xffffffffu, roll::nms_needs_diag(p, c, low1))) roll::nms_diag(p, up, c, dn, g);
-                        st = roll::nms_state(p, c, high1);
+                    if (__any_sync(0xffffffffu, roll::any_above(c, low))) {
+                        roll::NmsPartial p = roll::nms_axis(up, c, dn, g, low, s_tab);
+                        if (__any_sync(0xffffffffu, roll::nms_needs_diag(p))) roll::nms_diag(p, up, c, dn, g);
+                        st = roll::nms_state(p, c, high);
                     }
                     if (store_lane) {
                         weak_seen |= st & ~(st >> 1);
@@ -410,9 +414,13 @@ int canny_states(const MapSet &ms, const Dims &dims, int channels, uint8_t *stat
         const long long total = (long long)maps * strips_x * strips_y;
         I2S_ARG(total < (1ll << 31));
         const unsigned blocks = (unsigned)((total + CR_WARPS - 1) / CR_WARPS);
-        // "m > low" as "m >= low + 1" on 16-bit halves; magnitudes never exceed 2040
-        const uint32_t l1 = (uint32_t)min(max(low + 1, 0), 0xffff), h1 = (uint32_t)min(max(high + 1, 0), 0xffff);
-        const uint32_t low1 = l1 | (l1 << 16), high1 = h1 | (h1 << 16);
+        // thresholds as half2 constants, clamped to [-1, 2047]: magnitudes are integers in 0 .. 2040
+        auto half2_of = [](int v) {
+            const __half hv = __float2half((float)min(max(v, -1), 2047));
+            const uint32_t b = (uint32_t)__half_as_ushort(hv);
+            return (roll::h2)(b | (b << 16));
+        };
+        const roll::h2 low1 = half2_of(low), high1 = half2_of(high);
         I2S_CUDA(cudaMemsetAsync(flags, 0, align_up(tiles, 256) * 2, st));
         if (channels == 1)      // 5 resident blocks (no spills) measured 2 % faster than 6 (80 registers, a few spilled words)
             k_canny_roll<1, 5><<<blocks, CR_WARPS * 32, 0, st>>>(ms, dims, state, spitch, sstride, low1, high1, strips_x, strips_y,

@@ -10,6 +10,7 @@
 #include <stdint.h>
 
 #if defined(__CUDACC__)
+#include <cuda_fp16.h>
 #define I2S_HD __host__ __device__ __forceinline__
 #else
 #define I2S_HD inline
@@ -122,10 +123,151 @@ I2S_HD uint32_t gauss_h7(uint32_t Em2, uint32_t Em1, uint32_t E0, uint32_t E1, u
     return pack_q16(r0, r1, r2, r3);
 }
 
+// ------------------------------------------------------------------ packed half-precision helpers
+// Gradients (|d| <= 1020), magnitudes (<= 2040) and the sector quantities are small integers, exact in
+// fp16: from the column sums on, the Sobel / NMS arithmetic runs as half2 operations (HADD2 / HFMA2 /
+// HSET2 on the FMA pipe) instead of packed 16-bit integer min/max/logic on the half-rate ALU pipe.
+// `h2` is the bit pattern of a half2 (low half = left pixel of the pair).  On the host the same
+// functions are evaluated through float (exact for these ranges) so that tests/host/roll_host.cpp
+// runs the identical dataflow.
+typedef uint32_t h2;
+
+#if !defined(__CUDA_ARCH__)
+inline float half_bits_to_float(uint32_t hb)
+{
+    const uint32_t sign = (hb >> 15) & 1u, exp = (hb >> 10) & 31u, man = hb & 1023u;
+    float v;
+    if (exp == 0) v = (float)man * (1.0f / 16777216.0f);                    // subnormal: man * 2^-24
+    else if (exp == 31) v = man ? __builtin_nanf("") : __builtin_inff();
+    else {
+        v = (float)(1024u + man);
+        int e = (int)exp - 25;                                               // (1024 + man) * 2^(exp-25)
+        while (e > 0) { v *= 2.0f; e--; }
+        while (e < 0) { v *= 0.5f; e++; }
+    }
+    return sign ? -v : v;
+}
+inline uint32_t float_to_half_bits(float f)                                  // exact inputs only (integers, |f| <= 2048)
+{
+    _Float16 hv = (_Float16)f;
+    uint16_t b;
+    __builtin_memcpy(&b, &hv, 2);
+    return b;
+}
+inline h2 h2_make(float lo, float hi) { return float_to_half_bits(lo) | (float_to_half_bits(hi) << 16); }
+inline float h2_lo(h2 a) { return half_bits_to_float(a & 0xffffu); }
+inline float h2_hi(h2 a) { return half_bits_to_float(a >> 16); }
+#endif
+
+I2S_HD h2 h2_const(float v)                            // both halves = v (an exactly representable value)
+{
+#if defined(__CUDA_ARCH__)
+    const __half2 r = __float2half2_rn(v);
+    return *reinterpret_cast<const uint32_t *>(&r);
+#else
+    return h2_make(v, v);
+#endif
+}
+I2S_HD h2 h2_sub(h2 a, h2 b)
+{
+#if defined(__CUDA_ARCH__)
+    const __half2 r = __hsub2(*reinterpret_cast<const __half2 *>(&a), *reinterpret_cast<const __half2 *>(&b));
+    return *reinterpret_cast<const uint32_t *>(&r);
+#else
+    return h2_make(h2_lo(a) - h2_lo(b), h2_hi(a) - h2_hi(b));
+#endif
+}
+I2S_HD h2 h2_add(h2 a, h2 b)
+{
+#if defined(__CUDA_ARCH__)
+    const __half2 r = __hadd2(*reinterpret_cast<const __half2 *>(&a), *reinterpret_cast<const __half2 *>(&b));
+    return *reinterpret_cast<const uint32_t *>(&r);
+#else
+    return h2_make(h2_lo(a) + h2_lo(b), h2_hi(a) + h2_hi(b));
+#endif
+}
+I2S_HD h2 h2_mul(h2 a, h2 b)                           // only the SIGN of the result is used (overflow to inf is fine)
+{
+#if defined(__CUDA_ARCH__)
+    const __half2 r = __hmul2(*reinterpret_cast<const __half2 *>(&a), *reinterpret_cast<const __half2 *>(&b));
+    return *reinterpret_cast<const uint32_t *>(&r);
+#else
+    auto sgn = [](float x) { return x > 0 ? 1.0f : (x < 0 ? -1.0f : 0.0f); };
+    return h2_make(sgn(h2_lo(a)) * sgn(h2_lo(b)), sgn(h2_hi(a)) * sgn(h2_hi(b)));
+#endif
+}
+I2S_HD h2 h2_fma(h2 a, h2 b, h2 c)                     // a * b + c, exact for the operand ranges used here
+{
+#if defined(__CUDA_ARCH__)
+    const __half2 r = __hfma2(*reinterpret_cast<const __half2 *>(&a), *reinterpret_cast<const __half2 *>(&b),
+                              *reinterpret_cast<const __half2 *>(&c));
+    return *reinterpret_cast<const uint32_t *>(&r);
+#else
+    return h2_make(h2_lo(a) * h2_lo(b) + h2_lo(c), h2_hi(a) * h2_hi(b) + h2_hi(c));
+#endif
+}
+// 0xffff in every half where a > b / a >= b (HSET2.BM)
+I2S_HD uint32_t h2_gt(h2 a, h2 b)
+{
+#if defined(__CUDA_ARCH__)
+    return __hgt2_mask(*reinterpret_cast<const __half2 *>(&a), *reinterpret_cast<const __half2 *>(&b));
+#else
+    return (h2_lo(a) > h2_lo(b) ? 0xffffu : 0u) | (h2_hi(a) > h2_hi(b) ? 0xffff0000u : 0u);
+#endif
+}
+I2S_HD uint32_t h2_ge(h2 a, h2 b)
+{
+#if defined(__CUDA_ARCH__)
+    return __hge2_mask(*reinterpret_cast<const __half2 *>(&a), *reinterpret_cast<const __half2 *>(&b));
+#else
+    return (h2_lo(a) >= h2_lo(b) ? 0xffffu : 0u) | (h2_hi(a) >= h2_hi(b) ? 0xffff0000u : 0u);
+#endif
+}
+// |a| + |b|, |a| * k + |b|, |a| > b: the absolute values are written with the half2 intrinsic inside the
+// expression so that the compiler folds them into source modifiers of the consuming instruction
+I2S_HD h2 h2_addabs(h2 a, h2 b)
+{
+#if defined(__CUDA_ARCH__)
+    const __half2 r = __hadd2(__habs2(*reinterpret_cast<const __half2 *>(&a)), __habs2(*reinterpret_cast<const __half2 *>(&b)));
+    return *reinterpret_cast<const uint32_t *>(&r);
+#else
+    return h2_add(a & 0x7fff7fffu, b & 0x7fff7fffu);
+#endif
+}
+I2S_HD h2 h2_absadd(h2 a, h2 c)                        // |a| + c
+{
+#if defined(__CUDA_ARCH__)
+    const __half2 r = __hadd2(__habs2(*reinterpret_cast<const __half2 *>(&a)), *reinterpret_cast<const __half2 *>(&c));
+    return *reinterpret_cast<const uint32_t *>(&r);
+#else
+    return h2_add(a & 0x7fff7fffu, c);
+#endif
+}
+I2S_HD h2 h2_fma_abs(h2 a, h2 k, h2 b)                 // |a| * k + |b|
+{
+#if defined(__CUDA_ARCH__)
+    const __half2 r = __hfma2(__habs2(*reinterpret_cast<const __half2 *>(&a)), *reinterpret_cast<const __half2 *>(&k),
+                              __habs2(*reinterpret_cast<const __half2 *>(&b)));
+    return *reinterpret_cast<const uint32_t *>(&r);
+#else
+    return h2_fma(a & 0x7fff7fffu, k, b & 0x7fff7fffu);
+#endif
+}
+I2S_HD uint32_t h2_absgt(h2 a, h2 b)                   // |a| > b
+{
+#if defined(__CUDA_ARCH__)
+    return __hgt2_mask(__habs2(*reinterpret_cast<const __half2 *>(&a)), *reinterpret_cast<const __half2 *>(&b));
+#else
+    return h2_gt(a & 0x7fff7fffu, b);
+#endif
+}
+constexpr uint32_t H2_BIAS = 0x64006400u;              // 1024.0 in both halves: (v | H2_BIAS) is the half2 1024 + v for 0 <= v < 1024
+
 // ------------------------------------------------------------------ Sobel + L1 magnitude (A.4)
-// One pixel row of one channel, seen by a lane: its own word plus the words of the two neighbour lanes.  Kept per row: the three shifted pairs Nm = (p-1,p0), No = (p1,p2),
-// Np = (p3,p4) and the horizontal smoothing sA = (s0,s1), sB = (s2,s3), s_j = p[j-1]+2p[j]+p[j+1].
-struct SobelRow { uint32_t Nm, No, Np, sA, sB; };
+// One pixel row of one channel, seen by a lane: its own word plus the words of the two neighbour lanes.
+// Kept per row: the three shifted pairs Nm = (p-1,p0), No = (p1,p2), Np = (p3,p4) as 16-bit integers and
+// the horizontal smoothing s_j = p[j-1]+2p[j]+p[j+1] of pixels (0,1) / (2,3) as biased half2 (1024 + s).
+struct SobelRow { uint32_t Nm, No, Np; h2 sA, sB; };
 
 I2S_HD SobelRow sobel_row(uint32_t word, uint32_t left_word, uint32_t right_word)
 {
@@ -136,53 +278,57 @@ I2S_HD SobelRow sobel_row(uint32_t word, uint32_t left_word, uint32_t right_word
     r.Nm = prmt(left_word, lo, 0x5453);        // (p-1, p0)
     r.No = pair_mid(lo, hi);                   // (p1, p2)
     r.Np = prmt(hi, right_word, 0x1412);       // (p3, p4)
-    r.sA = r.Nm + r.No + lo + lo;
-    r.sB = r.No + r.Np + hi + hi;
+    r.sA = (r.Nm + r.No + lo + lo) | H2_BIAS;  // sums <= 1020
+    r.sB = (r.No + r.Np + hi + hi) | H2_BIAS;
     return r;
 }
 
-// Gradient of the middle row m from rows t (above), m, b (below): |dx|, |dy| per pixel as pairs
-// A = pixels 0,1 and B = pixels 2,3, and two "sign carriers": fx != 0 <=> dx < 0, fy != 0 <=> dy < 0
-// (per 16-bit half).
-struct Grad { uint32_t axA, axB, ayA, ayB, fxA, fxB, fyA, fyB; };
+// Gradient of the middle row m from rows t (above), m, b (below): signed dx, dy per pixel as half2,
+// pairs A = pixels 0,1 and B = pixels 2,3.  The biases of the operands cancel in the differences.
+struct Grad { h2 dxA, dxB, dyA, dyB; };
 
 I2S_HD Grad sobel_grad(const SobelRow &t, const SobelRow &m, const SobelRow &b)
 {
-    const uint32_t vNm = t.Nm + b.Nm + m.Nm + m.Nm;      // column sums at columns (-1,0)
-    const uint32_t vNo = t.No + b.No + m.No + m.No;      // (1,2)
-    const uint32_t vNp = t.Np + b.Np + m.Np + m.Np;      // (3,4)
+    const h2 vNm = (t.Nm + b.Nm + m.Nm + m.Nm) | H2_BIAS;      // column sums at columns (-1,0)
+    const h2 vNo = (t.No + b.No + m.No + m.No) | H2_BIAS;      // (1,2)
+    const h2 vNp = (t.Np + b.Np + m.Np + m.Np) | H2_BIAS;      // (3,4)
     Grad g;
-    uint32_t mx;
-    mx = max2(vNo, vNm); g.axA = mx - min2(vNo, vNm); g.fxA = mx ^ vNo;      // dx(0,1) = v(1,2) - v(-1,0)
-    mx = max2(vNp, vNo); g.axB = mx - min2(vNp, vNo); g.fxB = mx ^ vNp;      // dx(2,3) = v(3,4) - v(1,2)
-    mx = max2(b.sA, t.sA); g.ayA = mx - min2(b.sA, t.sA); g.fyA = mx ^ b.sA;  // dy = s(below) - s(above)
-    mx = max2(b.sB, t.sB); g.ayB = mx - min2(b.sB, t.sB); g.fyB = mx ^ b.sB;
+    g.dxA = h2_sub(vNo, vNm);                                   // dx(0,1) = v(1,2) - v(-1,0)
+    g.dxB = h2_sub(vNp, vNo);                                   // dx(2,3) = v(3,4) - v(1,2)
+    g.dyA = h2_sub(b.sA, t.sA);                                 // dy = s(below) - s(above)
+    g.dyB = h2_sub(b.sB, t.sB);
     return g;
 }
 
-// 3-channel Canny: per pixel keep the gradient of the channel with the largest |dx|+|dy|, the
-// first channel winning ties (cv.Canny on a colour image, img2sgf.py:162).  `cur`/`mcur` hold the
-// best so far and its magnitude pairs; `g` is the next channel.
-I2S_HD void grad_select(Grad &cur, uint32_t &mA, uint32_t &mB, const Grad &g)
+// L1 magnitude |dx| + |dy| (<= 2040, exact)
+I2S_HD void grad_mag(const Grad &g, h2 &mA, h2 &mB)
 {
-    const uint32_t gA = g.axA + g.ayA, gB = g.axB + g.ayB;
-    // take g where gA > mA  <=>  max(gA, mA + 1) == gA ... as a 0/0xffff mask per half
-    const uint32_t tA = min2(max2(gA, mA + ONE2) ^ gA, ONE2), tB = min2(max2(gB, mB + ONE2) ^ gB, ONE2);
-    const uint32_t kA = (tA ^ ONE2) * 0xffffu, kB = (tB ^ ONE2) * 0xffffu;    // 0xffff where g wins
-    cur.axA = (g.axA & kA) | (cur.axA & ~kA); cur.axB = (g.axB & kB) | (cur.axB & ~kB);
-    cur.ayA = (g.ayA & kA) | (cur.ayA & ~kA); cur.ayB = (g.ayB & kB) | (cur.ayB & ~kB);
-    cur.fxA = (g.fxA & kA) | (cur.fxA & ~kA); cur.fxB = (g.fxB & kB) | (cur.fxB & ~kB);
-    cur.fyA = (g.fyA & kA) | (cur.fyA & ~kA); cur.fyB = (g.fyB & kB) | (cur.fyB & ~kB);
-    mA = (gA & kA) | (mA & ~kA);
-    mB = (gB & kB) | (mB & ~kB);
+    mA = h2_addabs(g.dxA, g.dyA);
+    mB = h2_addabs(g.dxB, g.dyB);
+}
+
+I2S_HD uint32_t bitsel(uint32_t k, uint32_t a, uint32_t b) { return (a & k) | (b & ~k); }   // k ? a : b, one LOP3
+
+// 3-channel Canny: per pixel keep the gradient of the channel with the largest |dx|+|dy|, the
+// first channel winning ties (cv.Canny on a colour image, img2sgf.py:162).  `cur`/`mA,mB` hold the
+// best so far and its magnitude; `g` is the next channel.
+I2S_HD void grad_select(Grad &cur, h2 &mA, h2 &mB, const Grad &g)
+{
+    h2 gA, gB;
+    grad_mag(g, gA, gB);
+    const uint32_t kA = h2_gt(gA, mA), kB = h2_gt(gB, mB);     // 0xffff where g wins
+    cur.dxA = bitsel(kA, g.dxA, cur.dxA); cur.dxB = bitsel(kB, g.dxB, cur.dxB);
+    cur.dyA = bitsel(kA, g.dyA, cur.dyA); cur.dyB = bitsel(kB, g.dyB, cur.dyB);
+    mA = bitsel(kA, gA, mA);
+    mB = bitsel(kB, gB, mB);
 }
 
 // ------------------------------------------------------------------ non-maximum suppression (A.4)
 // A magnitude row as seen by a lane: A = (m0,m1), B = (m2,m3) plus the shifted pairs
-// Cm = (m-1,m0), Co = (m1,m2), Cp = (m3,m4) once the neighbour lanes' magnitudes are known.
-struct MagRow { uint32_t A, B, Cm, Co, Cp; };
+// Cm = (m-1,m0), Co = (m1,m2), Cp = (m3,m4) once the neighbour lanes' magnitudes are known (half2).
+struct MagRow { h2 A, B, Cm, Co, Cp; };
 
-I2S_HD MagRow mag_row(uint32_t A, uint32_t B, uint32_t leftB, uint32_t rightA)
+I2S_HD MagRow mag_row(h2 A, h2 B, h2 leftB, h2 rightA)
 {
     MagRow r;
     r.A = A; r.B = B;
@@ -192,86 +338,76 @@ I2S_HD MagRow mag_row(uint32_t A, uint32_t B, uint32_t leftB, uint32_t rightA)
     return r;
 }
 
-// 0xffff in every half where v != 0
-I2S_HD uint32_t nz_mask(uint32_t v) { return min2(v, ONE2) * 0xffffu; }
-
-// Fail value of "m > a && m >= b" per half: zero where the test passes.
-I2S_HD uint32_t fail_gt_ge(uint32_t m, uint32_t a, uint32_t b) { return max2(max2(a + ONE2, b), m) ^ m; }
-// Fail value of "m > a && m > b"
-I2S_HD uint32_t fail_gt_gt(uint32_t m, uint32_t a, uint32_t b) { return max2(max2(a, b) + ONE2, m) ^ m; }
-
-// Sector of the gradient direction per half, from |dx| = ax and |dy| = ay (both <= 1020):
+// Sector of the gradient direction, from ax = |dx| and ay = |dy| (both <= 1020):
 //   horizontal  <=>  (ay << 15) < ax * 13573                <=>  ay <= hp,  hp = floor(ax*13573 / 2^15)
-//   vertical    <=>  (ay << 15) > ax * 13573 + (ax << 16)   <=>  ay > 2 ax + hp
-// (13573 = 53*256 + 5, so hp = (ax*53 + ((ax*5) >> 8)) >> 7 stays inside 16 bits; the two forms of
-// the horizontal test differ only when ax*13573 is a multiple of 2^15, i.e. ax = 0, where ay <= 0
-// means magnitude 0 and the pixel is no candidate anyway.)
-// Returns masks (0xffff per half): nh = NOT horizontal, v = vertical.
-I2S_HD void sector_masks(uint32_t ax, uint32_t ay, uint32_t &nh, uint32_t &v)
+//   vertical    <=>  (ay << 15) > ax * 13573 + (ax << 16)   <=>  ay - 2 ax > hp
+// (ax*13573 is a multiple of 2^15 only for ax = 0, where the two forms of the horizontal test differ at
+// ay = 0 alone: magnitude 0, no candidate.)  hp comes from a 1021-entry table of half bit patterns
+// (sector_table_entry), indexed with the integer ax recovered from the half by the 1024 bias.
+I2S_HD uint16_t sector_table_entry(int ax)
 {
-    // horizontal  <=>  ay <= floor(wq / 128), wq = ax*53 + ((ax*5) >> 8)  <=>  128 * min(ay, 511) <= wq
-    // (wq <= 54080, so an ay above 511 can never be horizontal and the product stays inside 16 bits)
-    const uint32_t wq = ax * 53u + prmt(ax * 5u, 0, 0x4341);
-    const uint32_t a128 = min2(ay, 0x01ff01ffu) * 128u;
-    nh = nz_mask(a128 - min2(a128, wq));                       // 128 ay > wq
-    // vertical  <=>  ay > 2 ax + floor(wq / 128)  <=>  128 (ay - 2 ax) > wq  (ay - 2ax clamped to 0..511)
-    const uint32_t two = ax + ax;
-    const uint32_t z128 = min2(ay - min2(ay, two), 0x01ff01ffu) * 128u;
-    v = nz_mask(z128 - min2(z128, wq | 0x007f007fu));          // 128 z > wq  <=>  128 z > (wq | 127)
+    const int hp = (ax * 13573) >> 15;                     // <= 422
+#if defined(__CUDA_ARCH__)
+    return __half_as_ushort(__int2half_rn(hp));
+#else
+    return (uint16_t)float_to_half_bits((float)hp);
+#endif
+}
+constexpr int SECTOR_TABLE = 1024;
+
+// masks (0xffff per half): nh = NOT horizontal, v = vertical
+I2S_HD void sector_masks(h2 dx, h2 dy, const uint16_t *tab, uint32_t &nh, uint32_t &v)
+{
+    const uint32_t axi = h2_absadd(dx, H2_BIAS) & 0x03ff03ffu;         // the two integers ax = |dx|
+    const h2 hp = (uint32_t)tab[axi & 0xffffu] | ((uint32_t)tab[axi >> 16] << 16);
+    nh = h2_absgt(dy, hp);                                               // ay > hp
+    v = h2_gt(h2_fma_abs(dx, h2_const(-2.0f), dy), hp);                  // ay - 2 ax > hp
 }
 
 // NMS + thresholds for the 4 pixels of a lane.  up/c/dn = magnitude rows y-1, y, y+1; g = gradient
-// of row y.  low1 = (low+1) in both halves, high1 likewise (saturated to 0xffff).
+// of row y; low / high = the thresholds in both halves (clamped to 2047: no magnitude exceeds 2040).
 // Returns the 4 state bytes: 0 none, 1 weak candidate, 3 strong candidate.
-// `need_diag` (out): some pixel of this lane sits in the diagonal sector and is above `low`;
-// the caller then calls nms_diag() -- kept separate so a warp can skip it when no lane needs it.
-struct NmsPartial { uint32_t FA, FB, dA, dB; };   // fail values so far; diagonal-sector masks
+// nms_diag() is kept separate so a warp can skip it when no lane has a diagonal candidate.
+struct NmsPartial { uint32_t PA, PB, dA, dB; };   // pass masks so far (axis sectors, above low); diagonal-sector candidates
 
-// some pixel of this lane has a magnitude above `low` (m >= low1)
-I2S_HD bool any_above(const MagRow &c, uint32_t low1)
-{
-    const uint32_t mx = max2(c.A, c.B);
-    return min2(max2(mx, low1) ^ mx, ONE2) != ONE2;
-}
+// some pixel of this lane has a magnitude above `low`
+I2S_HD bool any_above(const MagRow &c, h2 low) { return (h2_gt(c.A, low) | h2_gt(c.B, low)) != 0; }
 
-I2S_HD NmsPartial nms_axis(const MagRow &up, const MagRow &c, const MagRow &dn, const Grad &g, uint32_t low1)
+I2S_HD NmsPartial nms_axis(const MagRow &up, const MagRow &c, const MagRow &dn, const Grad &g, h2 low, const uint16_t *tab)
 {
     uint32_t nhA, vA, nhB, vB;
-    sector_masks(g.axA, g.ayA, nhA, vA);
-    sector_masks(g.axB, g.ayB, nhB, vB);
-    const uint32_t ThA = fail_gt_ge(c.A, c.Cm, c.Co), ThB = fail_gt_ge(c.B, c.Co, c.Cp);
-    const uint32_t TvA = fail_gt_ge(c.A, up.A, dn.A), TvB = fail_gt_ge(c.B, up.B, dn.B);
-    const uint32_t lowA = max2(c.A, low1) ^ c.A, lowB = max2(c.B, low1) ^ c.B;      // zero where m > low
+    sector_masks(g.dxA, g.dyA, tab, nhA, vA);
+    sector_masks(g.dxB, g.dyB, tab, nhB, vB);
+    const uint32_t lowA = h2_gt(c.A, low), lowB = h2_gt(c.B, low);
+    // horizontal: m > left && m >= right ; vertical: m > up && m >= down
+    const uint32_t hA = ~nhA & h2_gt(c.A, c.Cm) & h2_ge(c.A, c.Co), hB = ~nhB & h2_gt(c.B, c.Co) & h2_ge(c.B, c.Cp);
+    const uint32_t wA = vA & h2_gt(c.A, up.A) & h2_ge(c.A, dn.A), wB = vB & h2_gt(c.B, up.B) & h2_ge(c.B, dn.B);
     NmsPartial p;
-    p.FA = (ThA & ~nhA) | (TvA & vA) | lowA;
-    p.FB = (ThB & ~nhB) | (TvB & vB) | lowB;
-    p.dA = nhA & ~vA;                      // diagonal sector
-    p.dB = nhB & ~vB;
+    p.PA = (hA | wA) & lowA;
+    p.PB = (hB | wB) & lowB;
+    p.dA = nhA & ~vA & lowA;               // diagonal sector and above low
+    p.dB = nhB & ~vB & lowB;
     return p;
 }
 
-I2S_HD bool nms_needs_diag(const NmsPartial &p, const MagRow &c, uint32_t low1)
-{
-    const uint32_t lowA = max2(c.A, low1) ^ c.A, lowB = max2(c.B, low1) ^ c.B;
-    return ((p.dA & ~nz_mask(lowA)) | (p.dB & ~nz_mask(lowB))) != 0;
-}
+I2S_HD bool nms_needs_diag(const NmsPartial &p) { return (p.dA | p.dB) != 0; }
 
 // diagonal sector: same sign of dx,dy -> m > UL && m > DR ; opposite sign -> m > UR && m > DL
 I2S_HD void nms_diag(NmsPartial &p, const MagRow &up, const MagRow &c, const MagRow &dn, const Grad &g)
 {
-    const uint32_t sdA = nz_mask(g.fxA) ^ nz_mask(g.fyA), sdB = nz_mask(g.fxB) ^ nz_mask(g.fyB);   // signs differ
-    const uint32_t sameA = fail_gt_gt(c.A, up.Cm, dn.Co), sameB = fail_gt_gt(c.B, up.Co, dn.Cp);
-    const uint32_t oppA = fail_gt_gt(c.A, up.Co, dn.Cm), oppB = fail_gt_gt(c.B, up.Cp, dn.Co);
-    p.FA |= p.dA & ((oppA & sdA) | (sameA & ~sdA));
-    p.FB |= p.dB & ((oppB & sdB) | (sameB & ~sdB));
+    const h2 zero = 0u;
+    const uint32_t sdA = h2_gt(zero, h2_mul(g.dxA, g.dyA)), sdB = h2_gt(zero, h2_mul(g.dxB, g.dyB));   // signs differ
+    const uint32_t sameA = h2_gt(c.A, up.Cm) & h2_gt(c.A, dn.Co), sameB = h2_gt(c.B, up.Co) & h2_gt(c.B, dn.Cp);
+    const uint32_t oppA = h2_gt(c.A, up.Co) & h2_gt(c.A, dn.Cm), oppB = h2_gt(c.B, up.Cp) & h2_gt(c.B, dn.Co);
+    p.PA |= p.dA & bitsel(sdA, oppA, sameA);
+    p.PB |= p.dB & bitsel(sdB, oppB, sameB);
 }
 
-I2S_HD uint32_t nms_state(const NmsPartial &p, const MagRow &c, uint32_t high1)
+I2S_HD uint32_t nms_state(const NmsPartial &p, const MagRow &c, h2 high)
 {
-    // per half: 0 where rejected, else 3 - 2 * (m <= high)
-    const uint32_t nsA = min2(max2(c.A, high1) ^ c.A, ONE2), nsB = min2(max2(c.B, high1) ^ c.B, ONE2);
-    const uint32_t stA = (0x00030003u - nsA - nsA) & ~nz_mask(p.FA);
-    const uint32_t stB = (0x00030003u - nsB - nsB) & ~nz_mask(p.FB);
+    // per half: 0 where rejected, else 1 + 2 * (m > high)
+    const uint32_t stA = p.PA & ((h2_gt(c.A, high) & 0x00020002u) | 0x00010001u);
+    const uint32_t stB = p.PB & ((h2_gt(c.B, high) & 0x00020002u) | 0x00010001u);
     return prmt(stA, stB, 0x6420);
 }
 

@@ -79,8 +79,11 @@ extern "C" void rh_sobel_nms(const uint8_t *src, int ch, int h, int w, int low, 
 {
     const int TH = 128, OW = 120;
     const int strips_x = (w + OW - 1) / OW, strips_y = (h + TH - 1) / TH;
-    const uint32_t l1 = (uint32_t)std::min(std::max(low + 1, 0), 0xffff), h1 = (uint32_t)std::min(std::max(high + 1, 0), 0xffff);
-    const uint32_t low1 = l1 | (l1 << 16), high1 = h1 | (h1 << 16);
+    // thresholds as half2 constants (clamped like canny.cu does), sector table like the kernel's shared-memory copy
+    const float lf = (float)std::min(std::max(low, -1), 2047), hf = (float)std::min(std::max(high, -1), 2047);
+    const h2 low1 = h2_make(lf, lf), high1 = h2_make(hf, hf);
+    static uint16_t tab[SECTOR_TABLE];
+    for (int i = 0; i < SECTOR_TABLE; i++) tab[i] = sector_table_entry(i);
     for (int sy = 0; sy < strips_y; sy++)
         for (int sx = 0; sx < strips_x; sx++) {
             const int y0 = sy * TH, y1 = std::min(y0 + TH, h);
@@ -114,7 +117,8 @@ extern "C" void rh_sobel_nms(const uint8_t *src, int ch, int h, int w, int low, 
                             const uint32_t cmA = ((x >= 0 && x < w) ? 0xffffu : 0u) | ((x + 1 >= 0 && x + 1 < w) ? 0xffff0000u : 0u);
                             const uint32_t cmB = ((x + 2 >= 0 && x + 2 < w) ? 0xffffu : 0u) | ((x + 3 >= 0 && x + 3 < w) ? 0xffff0000u : 0u);
                             Grad g = sobel_grad(R[lane][(u + 1) % 3][0], R[lane][(u + 2) % 3][0], R[lane][u % 3][0]);
-                            uint32_t a = g.axA + g.ayA, b = g.axB + g.ayB;
+                            h2 a, b;
+                            grad_mag(g, a, b);
                             for (int c = 1; c < ch; c++) {
                                 Grad gc = sobel_grad(R[lane][(u + 1) % 3][c], R[lane][(u + 2) % 3][c], R[lane][u % 3][c]);
                                 grad_select(g, a, b, gc);
@@ -144,8 +148,8 @@ extern "C" void rh_sobel_nms(const uint8_t *src, int ch, int h, int w, int low, 
                         }
                         NmsPartial P[32];
                         for (int lane = 0; lane < 32; lane++) {
-                            P[lane] = nms_axis(M[lane][(u + 1) % 3], M[lane][(u + 2) % 3], M[lane][u % 3], G[lane][(u + 1) % 2], low1);
-                            any = any || nms_needs_diag(P[lane], M[lane][(u + 2) % 3], low1);
+                            P[lane] = nms_axis(M[lane][(u + 1) % 3], M[lane][(u + 2) % 3], M[lane][u % 3], G[lane][(u + 1) % 2], low1, tab);
+                            any = any || nms_needs_diag(P[lane]);
                         }
                         for (int lane = 1; lane <= 30; lane++) {
                             int x = sx * OW - 4 + 4 * lane;
