@@ -17,7 +17,7 @@ SO = os.path.join(LIBDIR, "libimg2sgf_b200.so")
 SOURCES = ["profile.cu", "preproc.cu", "canny.cu", "circles.cu", "lines.cu", "board.cu", "pipeline.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
-         "-Xcompiler", "-fPIC"]
+         "-Xcompiler", "-fPIC"] + os.environ.get("I2S_NVCC_FLAGS", "").split()      # e.g. -DI2S_CANNY1_MINB=6 for tuning runs
 
 
 def _stale() -> bool:

@@ -24,6 +24,12 @@ namespace i2s {
 // The 3-channel variant also writes the greyscale plane (cv.cvtColor(.., BGR2GRAY) on the
 // RGB-ordered array, img2sgf.py:153) from the words it has just loaded, so the RGB
 // input is read from HBM once.
+#ifndef I2S_CANNY1_MINB
+#define I2S_CANNY1_MINB 6               // 80 registers, two spilled words: measured 5 % faster than 5 blocks of 86
+#endif
+#ifndef I2S_CANNY3_MINB
+#define I2S_CANNY3_MINB 4
+#endif
 constexpr int HT = 128;                           // hysteresis tile edge (see hyst_tile)
 constexpr int CR_TH = HT, CR_OW = 120, CR_WARPS = 4;    // a strip spans exactly one row of hysteresis tiles
 
@@ -422,11 +428,11 @@ int canny_states(const MapSet &ms, const Dims &dims, int channels, uint8_t *stat
         };
         const roll::h2 low1 = half2_of(low), high1 = half2_of(high);
         I2S_CUDA(cudaMemsetAsync(flags, 0, align_up(tiles, 256) * 2, st));
-        if (channels == 1)      // 5 resident blocks (no spills) measured 2 % faster than 6 (80 registers, a few spilled words)
-            k_canny_roll<1, 5><<<blocks, CR_WARPS * 32, 0, st>>>(ms, dims, state, spitch, sstride, low1, high1, strips_x, strips_y,
+        if (channels == 1)      // resident blocks per SM: tuned on the GPU (I2S_CANNY1_MINB at build time)
+            k_canny_roll<1, I2S_CANNY1_MINB><<<blocks, CR_WARPS * 32, 0, st>>>(ms, dims, state, spitch, sstride, low1, high1, strips_x, strips_y,
                                                                  (int)total, flags, tiles_x, nullptr, 0, 0);
         else
-            k_canny_roll<3, 4><<<blocks, CR_WARPS * 32, 0, st>>>(ms, dims, state, spitch, sstride, low1, high1, strips_x, strips_y,
+            k_canny_roll<3, I2S_CANNY3_MINB><<<blocks, CR_WARPS * 32, 0, st>>>(ms, dims, state, spitch, sstride, low1, high1, strips_x, strips_y,
                                                                  (int)total, flags, tiles_x, grey, gpitch, gstride);
         I2S_CHECK_LAUNCH("k_canny_roll");
     }

@@ -131,7 +131,10 @@ constexpr int AT = 128;                      // tile edge in accumulator cells
 constexpr int AG = 2;                        // guard cells around the ring
 constexpr int AS = AT + 2 + 2 * AG;          // shared rows / used columns
 constexpr int AP = AS + 1;                   // shared pitch (odd: column walks are conflict free)
-constexpr int VOTE_THREADS = 512;
+#ifndef I2S_VOTE_UNROLL
+#define I2S_VOTE_UNROLL 4               // 2..5 measured alike, 8 and 16 slower (longer scalar tails)
+#endif
+constexpr int VOTE_THREADS = 512;            // 384 alike, 640 / 672 slower
 constexpr int VOTE_SMEM = AS * AP * 4;
 constexpr int VB = 7;                        // buckets per axis that can overlap a tile's region
 static_assert(AP < 256, "the pitch is a byte operand of the address dot product");
@@ -179,9 +182,10 @@ __device__ __forceinline__ void vote_item(int *s_acc, uint32_t s_base, uint2 e, 
     asm volatile("" : "+r"(bias));          // opaque: keeps the bias inside the running value instead of one add per vote
     uint32_t U = bias + (uint32_t)t_lo * (uint32_t)S;
     int t = t_lo;
-    for (; t + 7 <= t_hi; t += 8, U += 8u * (uint32_t)S) {
+    constexpr int UN = I2S_VOTE_UNROLL;
+    for (; t + UN - 1 <= t_hi; t += UN, U += (uint32_t)UN * (uint32_t)S) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) vote_at(a0, U + (uint32_t)k * (uint32_t)S);
+        for (int k = 0; k < UN; k++) vote_at(a0, U + (uint32_t)k * (uint32_t)S);
     }
     for (; t <= t_hi; t++, U += (uint32_t)S) vote_at(a0, U);
     if (t_lo <= 0 && t_hi >= 0) atomicAdd(s_acc + (y - cy0) * AP + (x - cx0), -1);
@@ -738,7 +742,9 @@ int hough_circles_maps(const MapSet &ms, const Dims &dims, float *mcirc, int32_t
     {
         ScopedSection sec(SEC_RADIUS, st);
         // (a variant with four centres per warp -- 8 lanes each, 16-bit bins -- cut the instruction count by
-        // 18 % but not the time: the loop over the bucket entries dominates, not the per-centre scan)
+        // 18 % but not the time; row-sorted bucket lists with per-row starts, so that a centre walks only the
+        // rows inside its window, scanned 37 % fewer entries but ran slower: shorter per-bucket loops leave more
+        // lanes idle, and the row-per-lane loads made the list kernel 10 % slower)
         k_radius<<<dim3(16, maps), RW * 32, 0, st>>>(edges, plane, dir, nbx, nby, dims, ms.n, cand, ncand, lim.cand_cap, est, nest,
                                                      status);
         I2S_CHECK_LAUNCH("k_radius");
