@@ -88,4 +88,5 @@ I2S_HD uint32_t settle_word(const uint32_t (&plane)[SH][GW + 1], int ty, int j)
     return ge | eq;
 }
 
+
 }  // namespace i2s

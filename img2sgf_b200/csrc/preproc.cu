@@ -246,85 +246,18 @@ int gauss357(const uint8_t *src, int spitch, size_t sstride, uint8_t *d3, uint8_
 }
 
 // ------------------------------------------------------------------ median (A.3)
-// Exact b x b median with BORDER_REPLICATE by bit-sliced rank selection.  The staged tile is
-// transposed once per block into eight 1-bit planes.  A thread then gathers, for each plane, the
-// window bits of its four adjacent output pixels (b rows x (b+3) columns, rows packed at
-// a stride of b+3 bits) and selects the median MSB-first: with C the set of still-possible window
-// elements and k the rank wanted inside C, the next result bit is 0 iff k < popc(C & ~plane), which
-// also narrows C.  No sorting network, no histogram.
-
-// Median of the B x B windows of 4 adjacent pixels (row ty, columns gx..gx+3 of the tile) from the bit
-// planes of a tile staged with a halo of RS rows / HX columns.  Warp-uniform control flow (one
-// __any_sync): call it with all 32 lanes.  Returns the 4 result bytes.
-template <int B, int RS, int HX, int SH, int GW>
-__device__ __forceinline__ uint32_t median4_planes(const uint32_t (&s_bits)[10][SH][GW + 1],
-                                                   const uint32_t (&s_set)[3][2][MT_H][MT_W / 32], int ty, int gx, bool live)
-{
-    constexpr int F = B + 3;                         // window columns of 4 adjacent pixels
-    constexpr int RPW = 32 / F;                      // window rows packed per 32-bit word
-    constexpr int NW = (B + RPW - 1) / RPW;          // words per window
-    constexpr int RO = RS - B / 2;                   // first window row inside the staged halo
-    // per-word masks of the B low bits of every packed row field
-    uint32_t fm[NW];
-#pragma unroll
-    for (int wd = 0; wd < NW; wd++) {
-        fm[wd] = 0;
-#pragma unroll
-        for (int r = wd * RPW; r < B && r < (wd + 1) * RPW; r++) fm[wd] |= ((1u << B) - 1u) << ((r - wd * RPW) * F);
-    }
-    const int start = gx + HX - B / 2, wi = start >> 5, sh = start & 31;
-    // window bits of one plane for the 4 adjacent pixels: rows packed at a stride of F bits
-    auto gather = [&](int pl, uint32_t (&P)[NW]) {
-#pragma unroll
-        for (int wd = 0; wd < NW; wd++) P[wd] = 0;
-#pragma unroll
-        for (int r = 0; r < B; r++) {
-            const uint32_t *rw = &s_bits[pl][ty + RO + r][wi];
-            uint32_t bits = __funnelshift_r(rw[0], rw[1], sh) & ((1u << F) - 1u);
-            P[r / RPW] |= bits << ((r % RPW) * F);
-        }
-    };
-    // Shortcut (exact): if more than half of the B*B window pixels equal 255 the median is 255, likewise
-    // for 0.  Printed diagrams are mostly saturated paper and ink, so most warps finish here.  The
-    // verdicts come from median_settle() as one bit per pixel.
-    constexpr int BI = B / 2 - 1;
-    const uint32_t m255 = (s_set[BI][0][ty][gx >> 5] >> (gx & 31)) & 0xfu;
-    const uint32_t m0 = (s_set[BI][1][ty][gx >> 5] >> (gx & 31)) & 0xfu;
-    uint32_t packed = ((m255 * 0x00204081u) & 0x01010101u) * 0xffu;      // 0xff in the bytes of the settled-255 pixels
-    const bool open = (m255 | m0) != 0xfu;           // some pixel of this thread still needs the selection
-    if (__any_sync(0xffffffffu, open && live)) {
-        uint32_t P[8][NW];
-#pragma unroll
-        for (int bit = 0; bit < 8; bit++) gather(bit, P[bit]);
-        packed = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            uint32_t C[NW];                          // candidate set, kept shifted to pixel j's window columns
-#pragma unroll
-            for (int wd = 0; wd < NW; wd++) C[wd] = fm[wd] << j;
-            int k = (B * B) / 2;
-            uint32_t val = 0;
-#pragma unroll
-            for (int bit = 7; bit >= 0; bit--) {
-                uint32_t Z[NW], O[NW];
-                int nz = 0;
-#pragma unroll
-                for (int wd = 0; wd < NW; wd++) {
-                    const uint32_t pj = P[bit][wd];
-                    Z[wd] = C[wd] & ~pj;
-                    O[wd] = C[wd] & pj;
-                    nz += __popc(Z[wd]);
-                }
-                const bool zero = k < nz;              // the median has a 0 in this bit
-#pragma unroll
-                for (int wd = 0; wd < NW; wd++) C[wd] = zero ? Z[wd] : O[wd];
-                if (!zero) { k -= nz; val |= 1u << bit; }
-            }
-            packed |= val << (8 * j);
-        }
-    }
-    return packed;
-}
+// Exact b x b medians with BORDER_REPLICATE, bit-sliced.  The staged tile is transposed once per block
+// into eight 1-bit planes (plus "== 255" and "== 0").
+//   * Saturated-window verdicts (settle_word, median_cores.cuh): more than half of the window pixels
+//     equal to 255 (0) => the median is 255 (0), evaluated for 32 pixels per logic instruction.  Printed
+//     diagrams are mostly saturated paper and ink: the verdicts settle 95-98 % of the pixels.
+//   * The 4-pixel groups that still hold an unsettled pixel (5-9 % on diagrams -- thin bands along the stone
+//     rims --, 40-65 % on noisy scans) are queued in shared memory and every lane finishes one group by
+//     MSB-first rank selection on the window bits (select_group), so the warps doing the expensive part
+//     are dense whatever the content.  (Also tried: rank selection for 32 pixels per thread with carry-save
+//     adder trees on whole words -- no POPC, 3.5x fewer instructions on noisy content, but 130 registers
+//     per thread: slower in practice.)
+constexpr int MED_THREADS = 256;
 
 template <int MASK, int RS, int HX, int SH, int GW>
 __device__ __forceinline__ void median_settle(const uint32_t (&s_bits)[10][SH][GW + 1], uint32_t (&s_set)[3][2][MT_H][MT_W / 32])
@@ -342,33 +275,102 @@ __device__ __forceinline__ void median_settle(const uint32_t (&s_bits)[10][SH][G
     }
 }
 
+// Rank selection for ONE group of 4 adjacent pixels (row ty, columns gx..gx+3 of the tile): for each plane
+// the window bits of the four pixels (B rows x (B+3) columns, rows packed at a stride of B+3 bits) are
+// gathered once; per pixel the median is selected MSB-first with C = the set of still-possible window
+// elements and k = the rank wanted inside C: the next result bit is 0 iff k < popc(C & ~plane).  The groups
+// are taken from a queue (see k_median), one per lane.
+template <int B, int RS, int HX, int SH, int GW>
+__device__ __forceinline__ uint32_t select_group(const uint32_t (&s_bits)[10][SH][GW + 1], int ty, int gx)
+{
+    constexpr int F = B + 3;                         // window columns of 4 adjacent pixels
+    constexpr int RPW = 32 / F;                      // window rows packed per 32-bit word
+    constexpr int NW = (B + RPW - 1) / RPW;          // words per window
+    constexpr int RO = RS - B / 2;                   // first window row inside the staged halo
+    uint32_t fm[NW];                                 // per-word masks of the B low bits of every packed row field
+#pragma unroll
+    for (int wd = 0; wd < NW; wd++) {
+        fm[wd] = 0;
+#pragma unroll
+        for (int r = wd * RPW; r < B && r < (wd + 1) * RPW; r++) fm[wd] |= ((1u << B) - 1u) << ((r - wd * RPW) * F);
+    }
+    const int start = gx + HX - B / 2, wi = start >> 5, sh = start & 31;
+    uint32_t P[8][NW];
+#pragma unroll
+    for (int bit = 0; bit < 8; bit++) {
+#pragma unroll
+        for (int wd = 0; wd < NW; wd++) P[bit][wd] = 0;
+#pragma unroll
+        for (int r = 0; r < B; r++) {
+            const uint32_t *rw = &s_bits[bit][ty + RO + r][wi];
+            const uint32_t bits = __funnelshift_r(rw[0], rw[1], sh) & ((1u << F) - 1u);
+            P[bit][r / RPW] |= bits << ((r % RPW) * F);
+        }
+    }
+    uint32_t packed = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint32_t C[NW];                              // candidate set, kept shifted to pixel j's window columns
+#pragma unroll
+        for (int wd = 0; wd < NW; wd++) C[wd] = fm[wd] << j;
+        int k = (B * B) / 2;
+        uint32_t val = 0;
+#pragma unroll
+        for (int bit = 7; bit >= 0; bit--) {
+            uint32_t Z[NW], O[NW];
+            int nz = 0;
+#pragma unroll
+            for (int wd = 0; wd < NW; wd++) {
+                const uint32_t pj = P[bit][wd];
+                Z[wd] = C[wd] & ~pj;
+                O[wd] = C[wd] & pj;
+                nz += __popc(Z[wd]);
+            }
+            const bool zero = k < nz;                // the median has a 0 in this bit
+#pragma unroll
+            for (int wd = 0; wd < NW; wd++) C[wd] = zero ? Z[wd] : O[wd];
+            if (!zero) { k -= nz; val |= 1u << bit; }
+        }
+        packed |= val << (8 * j);
+    }
+    return packed;
+}
+
 // MASK selects the window sizes computed from ONE staged tile and ONE set of bit planes:
 // bit 0 -> 3x3 into dst3, bit 1 -> 5x5 into dst5, bit 2 -> 7x7 into dst7.
-template <int MASK> __global__ void __launch_bounds__(256, 4) k_median(const uint8_t *__restrict__ src,
-                                                                    uint8_t *__restrict__ dst3, uint8_t *__restrict__ dst5,
-                                                                    uint8_t *__restrict__ dst7, const Dims dims, int spitch,
-                                                                    size_t sstride, int pitch, size_t stride)
+__device__ __forceinline__ void store_unit(uint8_t *row, int x, int w, int wlim, bool al, const uint32_t (&out)[8])
+{
+#pragma unroll
+    for (int g = 0; g < 8; g++)
+        if (x + 4 * g < w) store4(row, x + 4 * g, w, wlim, al, out[g]);
+}
+
+template <int MASK> __global__ void __launch_bounds__(MED_THREADS, 4) k_median(const uint8_t *__restrict__ src,
+                                                                         uint8_t *__restrict__ dst3, uint8_t *__restrict__ dst5,
+                                                                         uint8_t *__restrict__ dst7, const Dims dims, int spitch,
+                                                                         size_t sstride, int pitch, size_t stride)
 {
     constexpr int RS = (MASK & 4) ? 3 : (MASK & 2) ? 2 : 1, HX = 16;   // x halo 16: bulk-copy rows are 16-byte aligned
     constexpr int SW = MT_W + 2 * HX, SH = MT_H + 2 * RS;
     constexpr int GW = (SW + 31) / 32;               // 32-pixel groups per tile row
+    constexpr int WORDS = MT_W / 32, UNITS = MT_H * WORDS;
     __shared__ __align__(128) uint8_t s_in[SH * SW];
     __shared__ uint32_t s_bits[10][SH][GW + 1];      // planes 0..7: bits of the pixel; 8: pixel == 255; 9: pixel == 0
     __shared__ uint32_t s_set[3][2][MT_H][MT_W / 32]; // per window size: median settled at 255 / at 0, one bit per pixel
+    __shared__ uint16_t s_glist[3][UNITS * 8];       // per window size: the 4-pixel groups queued for select_group (unit << 3 | group)
+    __shared__ int s_ngrp[3];
     __shared__ uint64_t s_bar;
-    __shared__ int s_next;                           // next (window size, patch) item to hand out
     const int2 wh = dims.of(blockIdx.z);
     const int w = wh.x, h = wh.y;
     const int x0 = blockIdx.x * MT_W, y0 = blockIdx.y * MT_H;
     if (x0 >= w || y0 >= h) return;                  // tile outside this image (ragged batch)
     const uint8_t *img = src + blockIdx.z * sstride;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uintptr_t src_al = reinterpret_cast<uintptr_t>(src) | (uintptr_t)spitch | (uintptr_t)sstride;
     const bool al_in = (src_al & 3) == 0, bulk = (src_al & 15) == 0;
     const bool al = ((reinterpret_cast<uintptr_t>(dst3) | reinterpret_cast<uintptr_t>(dst5) | reinterpret_cast<uintptr_t>(dst7) |
                       (uintptr_t)pitch | (uintptr_t)stride) & 3) == 0;
     const int wlim = write_limit(w, pitch, 4);
-    if (threadIdx.x == 0) s_next = 0;
+    if (threadIdx.x < 3) s_ngrp[threadIdx.x] = 0;
     stage_tile_bulk(s_in, img, h, w, spitch, x0 - HX, y0 - RS, SW, SH, BORDER_REPLICATE, bulk, al_in, &s_bar);
     {   // bit planes: s_bits[b][row][g] bit i = bit b of tile pixel (row, 32 g + i).  A thread turns
         // 8 adjacent pixels into one byte of every plane: bit b of the 4 bytes of a word is gathered
@@ -392,26 +394,41 @@ template <int MASK> __global__ void __launch_bounds__(256, 4) k_median(const uin
     __syncthreads();
     median_settle<MASK, RS, HX, SH, GW>(s_bits, s_set);
     __syncthreads();
-    // A warp covers a compact 16 x 8 pixel patch (lane = 4-pixel group lane%4 of row lane/4), so that
-    // the saturated-window shortcut applies to whole warps as often as possible.  A patch costs ~100
-    // instructions when the shortcut settles it and ~2500 when it does not, so the (window size, patch)
-    // items are handed out dynamically, largest windows first: warps that finish early take more.
-    constexpr int PATCHES = (MT_W / 16) * (MT_H / 8);
-    constexpr int NSIZES = ((MASK >> 2) & 1) + ((MASK >> 1) & 1) + (MASK & 1);
-    while (true) {
-        int item = 0;
-        if (lane == 0) item = atomicAdd(&s_next, 1);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= NSIZES * PATCHES) break;
-        const int q = item % PATCHES;
-        int which = item / PATCHES;                  // index among the enabled sizes, 7 first
-        const int ty = (q / (MT_W / 16)) * 8 + (lane >> 2), gx = ((q % (MT_W / 16)) * 4 + (lane & 3)) * 4;
-        const int y = y0 + ty, x = x0 + gx;
-        const bool live = y < h && x < w;
-        const size_t o = blockIdx.z * stride + (size_t)y * pitch;
-        if (MASK & 4) { if (which == 0) { const uint32_t v = median4_planes<7, RS, HX, SH, GW>(s_bits, s_set, ty, gx, live); if (live) store4(dst7 + o, x, w, wlim, al, v); } which--; }
-        if (MASK & 2) { if (which == 0) { const uint32_t v = median4_planes<5, RS, HX, SH, GW>(s_bits, s_set, ty, gx, live); if (live) store4(dst5 + o, x, w, wlim, al, v); } which--; }
-        if (MASK & 1) { if (which == 0) { const uint32_t v = median4_planes<3, RS, HX, SH, GW>(s_bits, s_set, ty, gx, live); if (live) store4(dst3 + o, x, w, wlim, al, v); } which--; }
+    // One thread per (window size, row, 32-pixel word): write the verdict bytes of the 32 pixels (0 for the
+    // unsettled ones, for now) and queue the 4-pixel groups that hold an unsettled pixel.
+    for (int t = threadIdx.x; t < 3 * UNITS; t += blockDim.x) {
+        const int bi = 2 - t / UNITS, u = t % UNITS, ty = u / WORDS, j = u % WORDS;     // 7x7 first
+        if (!((MASK >> bi) & 1)) continue;
+        const int y = y0 + ty, x = x0 + 32 * j;
+        if (y >= h || x >= w) continue;
+        uint8_t *dst = bi == 2 ? dst7 : (bi == 1 ? dst5 : dst3);
+        const uint32_t m255 = s_set[bi][0][ty][j];
+        uint32_t un = ~(m255 | s_set[bi][1][ty][j]);                          // unsettled pixels
+        if (w - x < 32) un &= (1u << (w - x)) - 1u;                            // columns beyond the image do not count
+        un |= un >> 1; un |= un >> 2;                                          // bit 4g: group g has an unsettled pixel
+        const uint32_t gm = ((((un & 0x1111u) * 0x1248u) >> 12) & 0x0fu) | ((((un >> 16) & 0x1111u) * 0x1248u) >> 8 & 0xf0u);
+        uint32_t out[8];
+#pragma unroll
+        for (int g = 0; g < 8; g++) out[g] = ((((m255 >> (4 * g)) & 0xfu) * 0x00204081u) & 0x01010101u) * 0xffu;
+        store_unit(dst + blockIdx.z * stride + (size_t)y * pitch, x, w, wlim, al, out);
+        if (gm) {
+            int at = atomicAdd(&s_ngrp[bi], __popc(gm));
+            for (uint32_t m = gm; m; m &= m - 1) s_glist[bi][at++] = (uint16_t)((u << 3) | (__ffs(m) - 1));
+        }
+    }
+    __syncthreads();
+    // the queued groups of all sizes as one sequence, largest windows first: one group per lane
+    const int n7 = s_ngrp[2], n5 = s_ngrp[1], n3 = s_ngrp[0];
+    for (int i = threadIdx.x; i < n7 + n5 + n3; i += blockDim.x) {
+        const int bi = i < n7 ? 2 : (i < n7 + n5 ? 1 : 0);
+        const int e = s_glist[bi][i - (bi == 2 ? 0 : (bi == 1 ? n7 : n7 + n5))];
+        const int u = e >> 3, ty = u / WORDS, gx = 32 * (u % WORDS) + 4 * (e & 7);
+        uint8_t *dst = (bi == 2 ? dst7 : (bi == 1 ? dst5 : dst3)) + blockIdx.z * stride + (size_t)(y0 + ty) * pitch;
+        uint32_t v;
+        if (bi == 2) v = select_group<7, RS, HX, SH, GW>(s_bits, ty, gx);
+        else if (bi == 1) v = select_group<5, RS, HX, SH, GW>(s_bits, ty, gx);
+        else v = select_group<3, RS, HX, SH, GW>(s_bits, ty, gx);
+        store4(dst, x0 + gx, w, wlim, al, v);
     }
 }
 
@@ -492,7 +509,7 @@ int median357(const uint8_t *src, int spitch, size_t sstride, uint8_t *d3, uint8
     if (n == 0) return I2S_OK;
     dim3 grid(cdiv(dims.w, MT_W), cdiv(dims.h, MT_H), n);
     ScopedSection sec(SEC_MEDIAN, st);
-    k_median<7><<<grid, 256, 0, st>>>(src, d3, d5, d7, dims, spitch, sstride, pitch, stride);
+    k_median<7><<<grid, MED_THREADS, 0, st>>>(src, d3, d5, d7, dims, spitch, sstride, pitch, stride);
     I2S_CHECK_LAUNCH("k_median");
     return I2S_OK;
 }
@@ -572,8 +589,8 @@ extern "C" int i2s_median(const uint8_t *src, uint8_t *dst, int n, int h, int w,
     ScopedSection sec(SEC_MEDIAN, st);
     if (b == 1) I2S_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * stride, cudaMemcpyDeviceToDevice, st));
     else if (b == 3) k_median3_net<<<grid, 256, 0, st>>>(src, dst, dims, pitch, stride, pitch, stride);
-    else if (b == 5) k_median<2><<<grid, 256, 0, st>>>(src, nullptr, dst, nullptr, dims, pitch, stride, pitch, stride);
-    else k_median<4><<<grid, 256, 0, st>>>(src, nullptr, nullptr, dst, dims, pitch, stride, pitch, stride);
+    else if (b == 5) k_median<2><<<grid, MED_THREADS, 0, st>>>(src, nullptr, dst, nullptr, dims, pitch, stride, pitch, stride);
+    else k_median<4><<<grid, MED_THREADS, 0, st>>>(src, nullptr, nullptr, dst, dims, pitch, stride, pitch, stride);
     I2S_CHECK_LAUNCH("k_median");
     return I2S_OK;
 }
