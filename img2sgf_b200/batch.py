@@ -283,9 +283,11 @@ class RaggedRunner:
     together with its i2s_image_t descriptors, copied with ONE host->device transfer and processed by
     ONE i2s_pipeline call; groups alternate between CUDA streams.  Engines are cached per canvas size."""
 
-    def __init__(self, limits: N.Limits | None = None, streams: int = 2, max_group: int = 32):
+    def __init__(self, limits: N.Limits | None = None, streams: int = 2, max_group: int = 32, pack_threads: int = 8):
         if not torch.cuda.is_available():
             raise N.NativeError("img2sgf_b200 needs a CUDA device (there is no CPU fallback)")
+        from concurrent.futures import ThreadPoolExecutor
+        self._pool = ThreadPoolExecutor(max_workers=pack_threads) if pack_threads > 1 else None
         self.limits = limits
         self.max_group = max_group
         self.streams = [torch.cuda.Stream() for _ in range(max(1, streams))]
@@ -334,13 +336,19 @@ class RaggedRunner:
             desc[k] = (off, h, w, pitch, int(thresholds[i]) if thresholds is not None else 0)
             off = (off + h * pitch + 15) // 16 * 16
 
-        def fill(buf):
+        def fill_one(buf, k):
+            a = images[idx[k]]
+            h, w = a.shape[:2]
+            o, pitch = int(desc[k]["offset"]), int(desc[k]["pitch"])
+            buf[o:o + h * pitch].reshape(h, pitch)[:, :w * ch] = a.reshape(h, w * ch)
+
+        def fill(buf, pool=None):
             buf[:desc.nbytes] = desc.view(np.uint8)
-            for k, i in enumerate(idx):
-                a = images[i]
-                h, w = a.shape[:2]
-                o, pitch = int(desc[k]["offset"]), int(desc[k]["pitch"])
-                buf[o:o + h * pitch].reshape(h, pitch)[:, :w * ch] = a.reshape(h, w * ch)
+            if pool is None:
+                for k in range(len(idx)):
+                    fill_one(buf, k)
+            else:                                          # numpy copies release the GIL: pack images in parallel
+                list(pool.map(lambda k: fill_one(buf, k), range(len(idx))))
         return off, desc, ch, fill
 
     def process_images(self, images, line_threshold=None, black_threshold: int = 128, thresholds=None,
@@ -396,7 +404,7 @@ class RaggedRunner:
                 drain(slot)                              # the slot's staging and record buffers are free again
             nbytes, desc, ch, fill = self.pack(images, idx, thresholds)
             pinned, dev = self._buffers(slot, nbytes)
-            fill(pinned.numpy())
+            fill(pinned.numpy(), self._pool)
             eng = self._engine(slot, len(idx), int(desc["h"].max()), int(desc["w"].max()))
             stream = self.streams[slot]
             stream.wait_stream(main)

@@ -23,7 +23,10 @@ constexpr int CANNY_LOW = 50, CANNY_HIGH = 100;
 // and sx = cvRound(dx*1024/mag), sy likewise -- runs with all lanes busy.
 // No block-wide barrier.  Order inside a bucket is arbitrary; votes commute.
 constexpr int EB = 32;
-constexpr int EL_WARPS = 8;
+#ifndef I2S_EL_WARPS
+#define I2S_EL_WARPS 8
+#endif
+constexpr int EL_WARPS = I2S_EL_WARPS;
 
 __device__ __forceinline__ uint32_t edge_nibble(uint32_t v) { return (((v >> 1) & 0x01010101u) * 0x01020408u) >> 24; }
 
@@ -294,11 +297,30 @@ __device__ __forceinline__ float radius_of_q(int q)
     return __fadd_rn(__fdiv_rn(__fdiv_rn((float)q, 2.0f), 10.0f), 1.0f);
 }
 
+#ifndef I2S_RADIUS_GRIDX
+#define I2S_RADIUS_GRIDX 16
+#endif
 constexpr int RW = 8;          // warps per block
 constexpr int RBINS = 320;     // NBINS padded to a multiple of 32 (pad stays zero)
 constexpr int RQ = 576;        // radius table size: q = upbin + j <= 289 + 279
 
-__global__ void __launch_bounds__(RW * 32, 6) k_radius(const uint2 *__restrict__ edges, size_t estride,
+struct RadiusTables { float rtab[RQ]; uint16_t binlut[900]; };
+
+// Centres sit on half-integers and edge pixels on integers, so the float32 squared distance
+// (cx+.5-px)^2 + (cy+.5-py)^2 is exactly q + 0.5 with q = dx(dx+1) + dy(dy+1) an integer: the
+// sqrt / rint chain of SURVEY A.5 step 4 is tabulated over the 899 admissible q, once per call
+// (it used to be recomputed by every block: a fifth of the radius kernel's instructions).
+__global__ void __launch_bounds__(256) k_radius_tables(RadiusTables *t)
+{
+    for (int q = threadIdx.x; q < RQ; q += blockDim.x) t->rtab[q] = radius_of_q(q);
+    for (int q = threadIdx.x; q < 900; q += blockDim.x) {
+        const float dd = __fsqrt_rn((float)q + 0.5f);
+        const int bin = __float2int_rn(__fmul_rn(__fsub_rn(dd, 1.0f), 10.0f));
+        t->binlut[q] = (uint16_t)min(max(bin, 0), NBINS - 1);
+    }
+}
+
+__global__ void __launch_bounds__(RW * 32, 6) k_radius(const RadiusTables *__restrict__ tables, const uint2 *__restrict__ edges, size_t estride,
                                                    const int2 *__restrict__ dir, int nbx, int nby, const Dims dims,
                                                    int n_images, const int32_t *__restrict__ cand,
                                                    const int32_t *__restrict__ ncand, int cand_cap, unsigned long long *est,
@@ -308,7 +330,7 @@ __global__ void __launch_bounds__(RW * 32, 6) k_radius(const uint2 *__restrict__
     __shared__ int s_pref[RW][RBINS];
     __shared__ short s_nzp[RW][RBINS];             // highest non-empty bin at or below b (-1: none)
     __shared__ float s_rtab[RQ];
-    __shared__ uint16_t s_binlut[900];             // histogram bin of squared distance q + 0.5, q = 1..899
+    __shared__ __align__(4) uint16_t s_binlut[900];   // histogram bin of squared distance q + 0.5, q = 1..899
     const int map = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int n = ncand[map];
@@ -322,15 +344,10 @@ __global__ void __launch_bounds__(RW * 32, 6) k_radius(const uint2 *__restrict__
     const uint2 *elist = edges + map * estride;
     const int2 *mdir = dir + (size_t)map * nbx * nby;
     const int aw = w + 2;
-    for (int q = threadIdx.x; q < RQ; q += blockDim.x) s_rtab[q] = radius_of_q(q);
-    // Centres sit on half-integers and edge pixels on integers, so the float32 squared distance
-    // (cx+.5-px)^2 + (cy+.5-py)^2 is exactly q + 0.5 with q = dx(dx+1) + dy(dy+1) an integer: the
-    // sqrt / rint chain of SURVEY A.5 step 4 is tabulated once per block over the 899 admissible q.
-    for (int q = threadIdx.x; q < 900; q += blockDim.x) {
-        const float dd = __fsqrt_rn((float)q + 0.5f);
-        const int bin = __float2int_rn(__fmul_rn(__fsub_rn(dd, 1.0f), 10.0f));
-        s_binlut[q] = (uint16_t)min(max(bin, 0), NBINS - 1);
-    }
+    // the radius and distance-bin tables (k_radius_tables) from the workspace into shared memory
+    for (int q = threadIdx.x; q < RQ; q += blockDim.x) s_rtab[q] = __ldg(tables->rtab + q);
+    for (int q = threadIdx.x; q < 900 / 2; q += blockDim.x)
+        reinterpret_cast<uint32_t *>(s_binlut)[q] = __ldg(reinterpret_cast<const uint32_t *>(tables->binlut) + q);
     __syncthreads();
     int *bins = s_bins[warp], *pref = s_pref[warp];
     short *nzp = s_nzp[warp];
@@ -695,6 +712,7 @@ size_t circles_scratch_bytes(int maps, int h, int w, const i2s_limits_t &lim)
     b += align_up((size_t)maps * lim.cand_cap * 4, 256);            // candidate centres
     b += align_up((size_t)maps * lim.cand_cap * 8, 256);            // estimated circle keys
     b += align_up((size_t)maps * 4 * 4, 256);                       // counters
+    b += align_up(sizeof(RadiusTables), 256);
     if (lim.cand_cap > FINISH_SMEM_CAP) b += align_up((size_t)maps * finish_bytes_per_map(p2_of(lim.cand_cap)), 256);
     b += canny_scratch_bytes(maps, h, w);
     return b + 4096;
@@ -715,6 +733,7 @@ int hough_circles_maps(const MapSet &ms, const Dims &dims, float *mcirc, int32_t
     int32_t *cand = ar.take<int32_t>((size_t)maps * lim.cand_cap);
     unsigned long long *est = ar.take<unsigned long long>((size_t)maps * lim.cand_cap);
     int32_t *ctr = ar.take<int32_t>((size_t)maps * 3);
+    RadiusTables *rtables = ar.take<RadiusTables>(1);
     const int np2 = p2_of(lim.cand_cap);
     unsigned char *gbuf = lim.cand_cap > FINISH_SMEM_CAP ? ar.take<unsigned char>((size_t)maps * finish_bytes_per_map(np2)) : nullptr;
     void *cscratch = ar.take<uint8_t>(canny_scratch_bytes(maps, h, w));
@@ -745,7 +764,9 @@ int hough_circles_maps(const MapSet &ms, const Dims &dims, float *mcirc, int32_t
         // 18 % but not the time; row-sorted bucket lists with per-row starts, so that a centre walks only the
         // rows inside its window, scanned 37 % fewer entries but ran slower: shorter per-bucket loops leave more
         // lanes idle, and the row-per-lane loads made the list kernel 10 % slower)
-        k_radius<<<dim3(16, maps), RW * 32, 0, st>>>(edges, plane, dir, nbx, nby, dims, ms.n, cand, ncand, lim.cand_cap, est, nest,
+        k_radius_tables<<<1, 256, 0, st>>>(rtables);
+        I2S_CHECK_LAUNCH("k_radius_tables");
+        k_radius<<<dim3(I2S_RADIUS_GRIDX, maps), RW * 32, 0, st>>>(rtables, edges, plane, dir, nbx, nby, dims, ms.n, cand, ncand, lim.cand_cap, est, nest,
                                                      status);
         I2S_CHECK_LAUNCH("k_radius");
     }
