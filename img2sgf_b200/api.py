@@ -409,24 +409,41 @@ class Processed:
 
 def process_image(rgb: np.ndarray, threshold: int | None = None,
                   black_stone_threshold: int = black_stone_threshold_default, contrast_slider: float | None = None,
-                  brightness_slider: float | None = None) -> Processed:
+                  brightness_slider: float | None = None, selection=None) -> Processed:
     """process_image() (img2sgf.py:117-204) through find_grid() and identify_board() -- one i2s_pipeline
     call.  `rgb`: [h,w,3] u8 in PIL's RGB order, or [h,w] for a greyscale source.  By default the array
     is taken as already contrast-enhanced (:150); with `contrast_slider` / `brightness_slider` (the GUI's
-    0..100 values, defaults 70 / 50) the prologue :142-149 runs on the device first."""
+    0..100 values, defaults 70 / 50) the prologue :142-149 runs on the device first.
+
+    `selection` = (x0, y0, x1, y1): the crop of crop_and_rotate_image() (img2sgf.py:110-114, PIL box
+    convention, rotation 0) without copying pixels: the whole image is uploaded once and the pipeline is
+    handed a view of it -- an i2s_image_t with the offset of the box's first pixel and the full image's row
+    pitch.  (The GUI re-runs process_image on every rubber-band zoom, :677-723.)"""
     from .batch import Engine, make_params
     _require_cuda()
-    h, w = rgb.shape[:2]
+    H, W = rgb.shape[:2]
     ch = 1 if rgb.ndim == 2 else 3
+    x0, y0, x1, y1 = (0, 0, W, H) if selection is None else [int(v) for v in selection]
+    if not (0 <= x0 < x1 <= W and 0 <= y0 < y1 <= H):
+        raise ValueError("selection outside the image")
+    h, w = y1 - y0, x1 - x0
     if threshold is None:
         threshold = choose_threshold(w, h)
     fc = scaled_contrast(contrast_slider) if contrast_slider is not None else 1.0
     fb = scaled_brightness(brightness_slider) if brightness_slider is not None else 1.0
     params = make_params(threshold, black_stone_threshold, contrast_factor=fc, brightness_factor=fb)
+    full = np.ascontiguousarray(rgb, np.uint8)
 
     def run(lim):
         eng = Engine(1, h, w, limits=lim, taps=True)
-        recs = eng.run_host(np.ascontiguousarray(rgb, np.uint8)[None], params, channels=ch)
+        if selection is None:
+            recs = eng.run_host(full[None], params, channels=ch)
+        else:
+            desc = np.zeros(1, N.IMAGE_DTYPE)
+            desc[0] = ((y0 * W + x0) * ch, h, w, W * ch, 0)
+            d_img, d_desc = _dev(full), _dev(desc.view(np.uint8))
+            recs = eng.run(d_img.reshape(-1), params, n=1, channels=ch, images=d_desc).cpu().numpy() \
+                      .view(N.RECORD_DTYPE).reshape(1)
         return (eng, recs), int(recs[0]["status"])
 
     eng, recs = _retrying(run)

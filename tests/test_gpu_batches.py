@@ -287,3 +287,44 @@ def test_hysteresis_many_passes(api, oracle):
         img[y:y + 12, 10:690] = 146
     img[20:32, 10:40] = 255
     assert np.array_equal(api.canny_grey(img, 50, 100, hyst_passes=130), oracle.canny_grey(img, 50, 100))
+
+
+# ------------------------------------------------------------------ crop as a view; records -> SGF
+def test_selection_is_a_view(api, oracle):
+    """crop_and_rotate_image (img2sgf.py:110-114) at rotation 0: process_image(selection=box) works on a view of
+    the uploaded image (offset + full-image pitch) and equals processing the cropped copy and the oracle."""
+    from img2sgf_b200 import synth
+    g, _ = synth.diagram(700, 30, 14, seed=11, noise=1.5)
+    rgb = synth.to_rgb(g)
+    for box in ((37, 21, 660, 655), (0, 0, 700, 700), (101, 203, 452, 517)):
+        x0, y0, x1, y1 = box
+        crop = np.ascontiguousarray(rgb[y0:y1, x0:x1])
+        a = api.process_image(rgb, selection=box)
+        b = api.process_image(crop)
+        assert a.record.tobytes() == b.record.tobytes(), box
+        assert np.array_equal(a.circles, b.circles) and np.array_equal(a.circles_removed_image_np, b.circles_removed_image_np)
+        res, circles, masked = oracle.pipeline(crop)
+        assert np.array_equal(a.circles, circles) and np.array_equal(a.circles_removed_image_np, masked), box
+    gv = api.process_image(np.ascontiguousarray(g), selection=(37, 21, 660, 655))       # greyscale source, cropped
+    assert gv.record.tobytes() == api.process_image(rgb, selection=(37, 21, 660, 655)).record.tobytes()
+
+
+def test_gpu_records_to_sgf(api, golden):
+    """the records of the GPU path through align_board + to_SGF (img2sgf_b200/sgf.py) equal the
+    reference's own output stage (replayed in oracle/ref_replay.py) applied to the golden boards."""
+    from img2sgf_b200 import batch as B, sgf
+    from oracle import ref_replay as R
+    imgs = [load_input(n) for n in FIXTURES]
+    rec = B.RaggedRunner().process_images(imgs)
+    texts = sgf.records_to_sgf(rec)
+    n = 0
+    for k, name in enumerate(FIXTURES):
+        if not bool(golden[name + "/board_ready"]):
+            assert texts[k] is None, name
+            continue
+        part = golden[name + "/board"].astype(np.float64)
+        hs, vs = part.shape
+        stm = 1 if int((part == 1).sum()) <= int((part == 2).sum()) else 2        # img2sgf.py:528-534
+        assert texts[k] == R.to_SGF(R.align_board(part, hs, vs), stm), name
+        n += 1
+    assert n >= 14
