@@ -175,16 +175,38 @@ __global__ void __launch_bounds__(CM_WARPS * 32) k_classify_mean(const uint8_t *
     py_slice(w, xmin, xmax);
     py_slice(h, ymin, ymax);
     const int ww = xmax - xmin, wh_ = ymax - ymin;
-    unsigned int sum = 0;                                                  // <= 255 * 16384^2 would overflow; windows are < 2^23 px
     unsigned long long sum64 = 0;
-    if (ww > 0 && wh_ > 0) {
-        const uint8_t *base = grey + img * stride + (size_t)ymin * pitch + xmin;
+    const uint8_t *plane = grey + img * stride;
+    if (ww > 0 && wh_ > 0 && (((uintptr_t)plane | (uint32_t)pitch) & 3u) == 0) {
+        // aligned 32-bit words, four pixels per dot product; the bytes of the first / last word outside
+        // [xmin, xmax) are masked off.  The warp is cut into rows of `lpr` lanes (the power of two that
+        // covers a window row) so that several rows are in flight per iteration.
+        const int xa = xmin & ~3, nwords = (xmax - xa + 3) >> 2;
+        int lsh = 5;
+        while (lsh > 0 && (16 >> (5 - lsh)) >= nwords) lsh--;              // lanes per row = 1 << lsh >= min(nwords, 32)
+        const int lpr = 1 << lsh, k0 = lane & (lpr - 1), rstep = 32 >> lsh;
+        const uint8_t *base = plane + (size_t)ymin * pitch + xa;
+#pragma unroll 4
+        for (int py = lane >> lsh; py < wh_; py += rstep) {
+            const uint32_t *row = reinterpret_cast<const uint32_t *>(base + (size_t)py * pitch);
+            unsigned int sum = 0;
+            for (int k = k0; k < nwords; k += lpr) {
+                uint32_t v = __ldg(row + k);
+                if (k == 0) v &= 0xffffffffu << (8 * (xmin - xa));
+                const int nb = xmax - (xa + 4 * k);
+                if (nb < 4) v &= (1u << (8 * nb)) - 1u;
+                sum = __dp4a(v, 0x01010101u, sum);
+            }
+            sum64 += sum;
+        }
+    } else if (ww > 0 && wh_ > 0) {
+        const uint8_t *base = plane + (size_t)ymin * pitch + xmin;
         for (int py = 0; py < wh_; py++) {
             const uint8_t *row = base + (size_t)py * pitch;
+            unsigned int sum = 0;
             for (int px = lane; px < ww; px += 32) sum += __ldg(row + px);
-            if ((py & 255) == 255) { sum64 += sum; sum = 0; }
+            sum64 += sum;
         }
-        sum64 += sum;
     }
     for (int o = 16; o > 0; o >>= 1) sum64 += __shfl_down_sync(0xffffffffu, sum64, o);
     if (lane == 0) {

@@ -55,10 +55,12 @@ extern "C" {
 #define I2S_ST_HYST_NOT_CONVERGED 8/* Canny hysteresis needs more passes             */
 #define I2S_ST_GRID_OVERFLOW 16    /* > I2S_MAX_GRID lines on an axis (board not ready anyway) */
 
+#define I2S_MAX_CIRCLE_CAP 65534    /* the masking kernel keeps 1 + circle index in 16 bits */
+
 /* limits used by the entry points (all data-dependent sizes) */
 typedef struct {
     int32_t cand_cap;      /* accumulator peaks per HoughCircles call (32 .. 16384)       */
-    int32_t circle_cap;    /* circles per image in the stacked output (rows of 3 floats) */
+    int32_t circle_cap;    /* circles per image in the stacked output (rows of 3 floats), <= I2S_MAX_CIRCLE_CAP */
     int32_t line_cap;      /* line peaks per direction per image (2 .. 4096)             */
     int32_t hyst_passes;   /* hysteresis pass budget (cross-tile propagation rounds)     */
 } i2s_limits_t;
