@@ -305,6 +305,10 @@ __device__ __forceinline__ float radius_of_q(int q)
 #define I2S_RADIUS_GRIDX 16
 #endif
 constexpr int RW = 8;          // warps per block
+#ifndef I2S_RADIUS_BATCH
+#define I2S_RADIUS_BATCH 4
+#endif
+constexpr int RB = I2S_RADIUS_BATCH;   // candidates per warp and round
 constexpr int RBINS = 320;     // NBINS padded to a multiple of 32 (pad stays zero)
 constexpr int RQ = 576;        // radius table size: q = upbin + j <= 289 + 279
 
@@ -324,15 +328,13 @@ __global__ void __launch_bounds__(256) k_radius_tables(RadiusTables *t)
     }
 }
 
-__global__ void __launch_bounds__(RW * 32, 6) k_radius(const RadiusTables *__restrict__ tables, const uint2 *__restrict__ edges, size_t estride,
+__global__ void __launch_bounds__(RW * 32, 5) k_radius(const RadiusTables *__restrict__ tables, const uint2 *__restrict__ edges, size_t estride,
                                                    const int2 *__restrict__ dir, int nbx, int nby, const Dims dims,
                                                    int n_images, const int32_t *__restrict__ cand,
                                                    const int32_t *__restrict__ ncand, int cand_cap, unsigned long long *est,
                                                    int32_t *nest, int32_t *status)
 {
-    __shared__ int s_bins[RW][RBINS];
-    __shared__ int s_pref[RW][RBINS];
-    __shared__ short s_nzp[RW][RBINS];             // highest non-empty bin at or below b (-1: none)
+    __shared__ __align__(16) int s_bins[RW][RB][RBINS];   // histograms, then (prefix sum << 16) | (1 + highest non-empty bin at or below)
     __shared__ float s_rtab[RQ];
     __shared__ __align__(4) uint16_t s_binlut[900];   // histogram bin of squared distance q + 0.5, q = 1..899
     const int map = blockIdx.y;
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(RW * 32, 6) k_radius(const RadiusTables *__res
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(status + map % n_images, I2S_ST_CAND_OVERFLOW);
         n = cand_cap;
     }
-    if (blockIdx.x * RW >= n) return;
+    if (blockIdx.x * RW * RB >= n) return;
     const int2 wh = dims.of(map % n_images);
     const int w = wh.x, h = wh.y;
     const uint2 *elist = edges + map * estride;
@@ -353,46 +355,75 @@ __global__ void __launch_bounds__(RW * 32, 6) k_radius(const RadiusTables *__res
     for (int q = threadIdx.x; q < 900 / 2; q += blockDim.x)
         reinterpret_cast<uint32_t *>(s_binlut)[q] = __ldg(reinterpret_cast<const uint32_t *>(tables->binlut) + q);
     __syncthreads();
-    int *bins = s_bins[warp], *pref = s_pref[warp];
-    short *nzp = s_nzp[warp];
-    for (int c = blockIdx.x * RW + warp; c < n; c += gridDim.x * RW) {
-        int base = cand[(size_t)map * cand_cap + c];
-        int cy = base / aw, cx = base - cy * aw;
-        for (int b = lane; b < RBINS; b += 32) bins[b] = 0;
-        __syncwarp();
-        // histogram of the distances to the edge pixels within 30 px: walk the edge-list buckets
-        // that overlap the 60x60 window (at most 3x3 of them).  (A finer 16x16 directory was tried:
-        // fewer entries to reject, but cells of ~18 entries leave half a warp idle -- slower.)
-        // Both differences travel in one register: (centre + 0x8000) - entry keeps the low half from
-        // borrowing, the xor turns it back into a signed 16-bit dx next to dy (|d| <= 92 inside 3x3
-        // buckets), and q = dx^2 + dy^2 + dx + dy is two 16-bit x 8-bit dot products.
-        const int xlo = max(cx - 29, 0), xhi = min(cx + 30, w - 1);
-        const int ylo = max(cy - 29, 0), yhi = min(cy + 30, h - 1);
-        const uint32_t cpk = (((uint32_t)cy << 16) | (uint32_t)cx) + 0x8000u;
-        auto tally = [&](uint32_t e) {
-            const int a = (int)((cpk - e) ^ 0x8000u);                        // (dy << 16) | (dx & 0xffff)
-            const int b = (int)__byte_perm((uint32_t)a, 0u, 0x4420);         // bytes (dx, dy)
-            const int q = __dp2a_lo(a, 0x0101, __dp2a_lo(a, b, 0));          // 1 <= r2 <= 900  <=>  1 <= q <= 899
-            if ((unsigned)(q - 1) < 899u) atomicAdd(bins + s_binlut[q], 1);
-        };
-        for (int by = ylo / EB; by <= yhi / EB; by++)
-            for (int bx = xlo / EB; bx <= xhi / EB; bx++) {
-                const int2 d = __ldg(mdir + by * nbx + bx);
-                // two list entries per lane and round: the loop is bound by the latency of its loads
-                for (int i = lane; i < d.y; i += 64) {
-                    const uint32_t e0 = __ldg(&elist[d.x + i].x);
-                    const bool two = i + 32 < d.y;
-                    const uint32_t e1 = two ? __ldg(&elist[d.x + i + 32].x) : 0u;
-                    tally(e0);
-                    if (two) tally(e1);
-                }
-            }
-        __syncwarp();
-        // inclusive prefix sums (10 bins per lane) and, per bin, the highest non-empty bin at or below it
+    // A warp takes RB consecutive candidates per round: their histograms are filled one after the other
+    // by all lanes, then the window scans -- a sequential walk per candidate -- run side by side, one
+    // candidate per lane, instead of one after the other with 32 lanes computing the same thing.
+    for (int c0 = (blockIdx.x * RW + warp) * RB; c0 < n; c0 += gridDim.x * RW * RB) {
+        const int nc = min(RB, n - c0);
+        const int mybase = lane < nc ? cand[(size_t)map * cand_cap + c0 + lane] : 0;
         {
-            int loc[10], sum = 0, top = -1;
+            uint4 *z = reinterpret_cast<uint4 *>(&s_bins[warp][0][0]);
+            for (int i = lane; i < RB * RBINS / 4; i += 32) z[i] = make_uint4(0, 0, 0, 0);
+        }
+        __syncwarp();
+        for (int k = 0; k < nc; k++) {
+            int *bins = s_bins[warp][k];
+            const int base = __shfl_sync(0xffffffffu, mybase, k);
+            const int cy = base / aw, cx = base - cy * aw;
+            // histogram of the distances to the edge pixels within 30 px: walk the edge-list buckets
+            // that overlap the 60x60 window (at most 3x3 of them).  (A finer 16x16 directory was tried:
+            // fewer entries to reject, but cells of ~18 entries leave half a warp idle -- slower.)
+            // Both differences travel in one register: (centre + 0x8000) - entry keeps the low half from
+            // borrowing, the xor turns it back into a signed 16-bit dx next to dy (|d| <= 92 inside 3x3
+            // buckets), and q = dx^2 + dy^2 + dx + dy is two 16-bit x 8-bit dot products.
+            const int xlo = max(cx - 29, 0), xhi = min(cx + 30, w - 1);
+            const int ylo = max(cy - 29, 0), yhi = min(cy + 30, h - 1);
+            const uint32_t cpk = (((uint32_t)cy << 16) | (uint32_t)cx) + 0x8000u;
+            auto tally = [&](uint32_t e) {
+                const int a = (int)((cpk - e) ^ 0x8000u);                        // (dy << 16) | (dx & 0xffff)
+                const int b = (int)__byte_perm((uint32_t)a, 0u, 0x4420);         // bytes (dx, dy)
+                const int q = __dp2a_lo(a, 0x0101, __dp2a_lo(a, b, 0));          // 1 <= r2 <= 900  <=>  1 <= q <= 899
+                if ((unsigned)(q - 1) < 899u) atomicAdd(bins + s_binlut[q], 1);
+            };
+            // The walk is bound by the latency of its loads, so they are issued in bulk: the (at most nine)
+            // directory entries by nine lanes at once, then per bucket row the first 64 entries of its three
+            // buckets -- six loads per lane in flight -- before any of them is tallied.  A lane without an
+            // entry tallies the centre itself (q = 0: rejected), so there is no branch around the tally.
+            const int bx0 = xlo / EB, by0 = ylo / EB, nbc = xhi / EB - bx0 + 1, nbr = yhi / EB - by0 + 1;   // <= 3 each
+            int2 dl = make_int2(0, 0);
+            if (lane < 9) {
+                const int r = lane / 3, c = lane - 3 * r;
+                if (r < nbr && c < nbc) dl = __ldg(mdir + (by0 + r) * nbx + bx0 + c);
+            }
+            const uint32_t none = cpk - 0x8000u;
+            for (int r = 0; r < nbr; r++) {
+                int off[3], cnt[3];
+                uint32_t e[6];
 #pragma unroll
-            for (int k = 0; k < 10; k++) { loc[k] = bins[lane * 10 + k]; sum += loc[k]; if (loc[k]) top = lane * 10 + k; }
+                for (int c = 0; c < 3; c++) {
+                    off[c] = __shfl_sync(0xffffffffu, dl.x, 3 * r + c);
+                    cnt[c] = __shfl_sync(0xffffffffu, dl.y, 3 * r + c);
+                }
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    e[2 * c] = lane < cnt[c] ? __ldg(&elist[off[c] + lane].x) : none;
+                    e[2 * c + 1] = lane + 32 < cnt[c] ? __ldg(&elist[off[c] + lane + 32].x) : none;
+                }
+#pragma unroll
+                for (int i = 0; i < 6; i++) tally(e[i]);
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                    for (int i = lane + 64; i < cnt[c]; i += 32) tally(__ldg(&elist[off[c] + i].x));
+            }
+        }
+        __syncwarp();
+        // in place: inclusive prefix sums (10 bins per lane; at most 2827 pixels lie within 30 px) and, per
+        // bin, one plus the highest non-empty bin at or below it (0: none)
+        for (int k = 0; k < nc; k++) {
+            int *bins = s_bins[warp][k];
+            int loc[10], sum = 0, top = 0;
+#pragma unroll
+            for (int i = 0; i < 10; i++) { loc[i] = bins[lane * 10 + i]; sum += loc[i]; if (loc[i]) top = lane * 10 + i + 1; }
             int incl = sum, below = top;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -400,41 +431,44 @@ __global__ void __launch_bounds__(RW * 32, 6) k_radius(const RadiusTables *__res
                 if (lane >= o) { incl += t; below = max(below, u); }
             }
             below = __shfl_up_sync(0xffffffffu, below, 1);                   // over the lanes before this one
-            if (lane == 0) below = -1;
+            if (lane == 0) below = 0;
             int run = incl - sum;
 #pragma unroll
-            for (int k = 0; k < 10; k++) {
-                run += loc[k];
-                pref[lane * 10 + k] = run;
-                if (loc[k]) below = lane * 10 + k;
-                nzp[lane * 10 + k] = (short)below;
+            for (int i = 0; i < 10; i++) {
+                run += loc[i];
+                if (loc[i]) below = lane * 10 + i + 1;
+                bins[lane * 10 + i] = (run << 16) | below;
             }
         }
         __syncwarp();
         // OpenCV's scan from the top bin: every non-zero bin opens a 10-bin window, the bin just below
-        // the window is skipped.  Uniform across lanes.
-        int maxCount = 0, bestq = 0;
-        float rBest = 0.0f;
-        int j = NBINS - 1;
-        while (j > 0) {
-            const int up = nzp[j];
-            if (up <= 0) break;
-            int jn = up - 10, cur;
-            if (jn >= 0) cur = pref[up] - pref[jn];
-            else { cur = pref[up]; jn = -1; }
-            float rCur = s_rtab[up + jn];
-            if ((__fmul_rn((float)cur, rBest) >= __fmul_rn((float)maxCount, rCur)) ||
-                (rBest < 1.1920929e-07f && cur >= maxCount)) {
-                rBest = rCur; maxCount = cur; bestq = up + jn;
+        // the window is skipped.  Lane k walks candidate k.
+        if (lane < nc) {
+            const uint32_t *P = reinterpret_cast<const uint32_t *>(s_bins[warp][lane]);
+            int maxCount = 0, bestq = 0;
+            float rBest = 0.0f;
+            int j = NBINS - 1;
+            while (j > 0) {
+                const int up = (int)(P[j] & 0xffffu) - 1;
+                if (up <= 0) break;
+                int jn = up - 10, cur = (int)(P[up] >> 16);
+                if (jn >= 0) cur -= (int)(P[jn] >> 16);
+                else jn = -1;
+                float rCur = s_rtab[up + jn];
+                if ((__fmul_rn((float)cur, rBest) >= __fmul_rn((float)maxCount, rCur)) ||
+                    (rBest < 1.1920929e-07f && cur >= maxCount)) {
+                    rBest = rCur; maxCount = cur; bestq = up + jn;
+                }
+                j = jn - 1;
             }
-            j = jn - 1;
-        }
-        if (lane == 0 && maxCount > ACC_THR) {
-            int slot = atomicAdd(nest + map, 1);
-            if (slot < cand_cap)
-                est[(size_t)map * cand_cap + slot] = ((unsigned long long)(4095 - maxCount) << 38) |
-                                                     ((unsigned long long)(1023 - bestq) << 28) |
-                                                     ((unsigned long long)cx << 14) | (unsigned long long)cy;
+            if (maxCount > ACC_THR) {
+                const int cy = mybase / aw, cx = mybase - cy * aw;
+                int slot = atomicAdd(nest + map, 1);
+                if (slot < cand_cap)
+                    est[(size_t)map * cand_cap + slot] = ((unsigned long long)(4095 - maxCount) << 38) |
+                                                         ((unsigned long long)(1023 - bestq) << 28) |
+                                                         ((unsigned long long)cx << 14) | (unsigned long long)cy;
+            }
         }
         __syncwarp();
     }
