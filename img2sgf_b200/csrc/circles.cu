@@ -33,7 +33,7 @@ constexpr int EL_WARPS = I2S_EL_WARPS;
 
 __device__ __forceinline__ uint32_t edge_nibble(uint32_t v) { return (((v >> 1) & 0x01010101u) * 0x01020408u) >> 24; }
 
-__global__ void __launch_bounds__(EL_WARPS * 32) k_edge_list(const MapSet ms, const Dims dims, const uint8_t *__restrict__ state,
+__global__ void __launch_bounds__(EL_WARPS * 32, 2048 / (EL_WARPS * 32)) k_edge_list(const MapSet ms, const Dims dims, const uint8_t *__restrict__ state,
                                                             int spitch, size_t sstride, uint2 *__restrict__ edges, size_t estride,
                                                             int32_t *ecount, int2 *dir, int nbx, int nby)
 {
@@ -66,13 +66,18 @@ __global__ void __launch_bounds__(EL_WARPS * 32) k_edge_list(const MapSet ms, co
         if (lane >= o) incl += t;
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
+    // One elected lane reserves the bucket's slice.  The reply is not needed before the first store, so the
+    // atomic's round trip overlaps the gradient loads below instead of preceding them.  (elect.sync: behind
+    // a plain `lane == 0` test ptxas aggregates the atomic across the "active" lanes and reads the reply
+    // back at once.)
     int off = 0;
-    if (lane == 0) {
-        off = total ? atomicAdd(ecount + map, total) : 0;
-        dir[((size_t)map * nby + by) * nbx + bx] = make_int2(off, total);
+    uint32_t leader = 0;
+    if (total == 0) {
+        if (lane == 0) dir[((size_t)map * nby + by) * nbx + bx] = make_int2(0, 0);
+        return;
     }
-    if (total == 0) return;
-    off = __shfl_sync(0xffffffffu, off, 0);
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync %1|p, 0xffffffff;\n\t@p atom.global.add.u32 %0, [%2], %3;\n\t}"
+                 : "+r"(off), "=r"(leader) : "l"(ecount + map), "r"(total) : "memory");
     uint16_t *lst = s_pos[warp];
     {
         int p = incl - c;
@@ -86,8 +91,7 @@ __global__ void __launch_bounds__(EL_WARPS * 32) k_edge_list(const MapSet ms, co
     __syncwarp();
     int ipitch;
     const uint8_t *img = ms.plane(map, ipitch);
-    uint2 *out = edges + map * estride + off;
-    for (int i = lane; i < total; i += 32) {
+    auto entry = [&](int i) -> uint2 {
         const int pos = lst[i];
         const int px = bx * EB + (pos & 31), py = by * EB + (pos >> 5);
         // Sobel 3x3, replicate border (A.4)
@@ -108,8 +112,18 @@ __global__ void __launch_bounds__(EL_WARPS * 32) k_edge_list(const MapSet ms, co
                 sy = __float2int_rn(__fdiv_rn(__fmul_rn(vy, 1024.0f), mag));
             }
         }
-        out[i] = make_uint2(((uint32_t)py << 16) | (uint32_t)px, (uint32_t)(sx & 0xffff) | ((uint32_t)sy << 16));   // (0,0) step = no vote
-    }
+        return make_uint2(((uint32_t)py << 16) | (uint32_t)px, (uint32_t)(sx & 0xffff) | ((uint32_t)sy << 16));   // (0,0) step = no vote
+    };
+    // the first two rounds (a bucket holds 56 edge pixels on average) before the offset is looked at
+    uint2 v0 = make_uint2(0, 0), v1 = make_uint2(0, 0);
+    if (lane < total) v0 = entry(lane);
+    if (lane + 32 < total) v1 = entry(lane + 32);
+    off = __shfl_sync(0xffffffffu, off, leader);
+    if (lane == 0) dir[((size_t)map * nby + by) * nbx + bx] = make_int2(off, total);
+    uint2 *out = edges + map * estride + off;
+    if (lane < total) out[lane] = v0;
+    if (lane + 32 < total) out[lane + 32] = v1;
+    for (int i = lane + 64; i < total; i += 32) out[i] = entry(i);
 }
 
 // ------------------------------------------------------------------ K5+K6: voting fused with peak finding
