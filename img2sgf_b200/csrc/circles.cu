@@ -147,7 +147,8 @@ __global__ void __launch_bounds__(EL_WARPS * 32, 2048 / (EL_WARPS * 32)) k_edge_
 // |t*s| <= 30*1024 keeps each half inside its 16 bits, so a single 32-bit add steps both coordinates.
 // Bits 10..15 of each half are floor(t*s/1024) + 32; (U >> 8) & 0x00FC00FC holds four times those two
 // numbers in its 16-bit halves, and one 16-bit x 8-bit dot product (IDP.2A) with the byte pair
-// (1, pitch) turns that into the byte address of the cell.  Per vote: add, shift, and, dot, atomic.
+// (1, pitch) turns that into the byte address of the cell.  Per vote: add, shift, and, dot, atomic -- and
+// in the unrolled loop the shift and the AND are shared by two votes (vote_at2).
 constexpr int AT = 128;                      // tile edge in accumulator cells
 constexpr int AG = 2;                        // guard cells around the ring
 constexpr int AS = AT + 2 + 2 * AG;          // shared rows / used columns
@@ -175,7 +176,19 @@ __device__ __forceinline__ void vote_at(uint32_t a0, uint32_t U)
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
 }
 
-__device__ __forceinline__ void vote_item(int *s_acc, uint32_t s_base, uint2 e, int cx0, int cy0, int X0, int X1, int Y0, int Y1)
+// Two votes at once: one byte permute gathers the high bytes of the four halves of (U, V) -- (x, y) of the
+// first vote, (x, y) of the second --, one AND clears the two fraction bits under each, and a 4-way byte dot
+// product with (1, pitch, 0, 0) resp. (0, 0, 1, pitch) gives each address: 4 instructions per vote with the add.
+__device__ __forceinline__ void vote_at2(uint32_t a0, uint32_t U, uint32_t V, uint32_t W0, uint32_t W1)
+{
+    const uint32_t m = __byte_perm(U, V, 0x7531) & 0xFCFCFCFCu;
+    const uint32_t addr0 = __dp4a(m, W0, a0), addr1 = __dp4a(m, W1, a0);
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr0) : "memory");
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr1) : "memory");
+}
+
+__device__ __forceinline__ void vote_item(int *s_acc, uint32_t s_base, uint2 e, int cx0, int cy0, int X0, int X1, int Y0, int Y1,
+                                          uint32_t W0, uint32_t W1)
 {
     const int x = e.x & 0xffff, y = e.x >> 16;
     const int sx = (int)(short)(e.y & 0xffff), sy = (int)e.y >> 16;
@@ -202,20 +215,23 @@ __device__ __forceinline__ void vote_item(int *s_acc, uint32_t s_base, uint2 e, 
     uint32_t bias = 0x80008000u;
     asm volatile("" : "+r"(bias));          // opaque: keeps the bias inside the running value instead of one add per vote
     uint32_t U = bias + (uint32_t)t_lo * (uint32_t)S;
-    int t = t_lo;
     constexpr int UN = I2S_VOTE_UNROLL;
-    for (; t + UN - 1 <= t_hi; t += UN, U += (uint32_t)UN * (uint32_t)S) {
+    const int nvotes = t_hi - t_lo + 1;
+    for (int i = nvotes / UN; i > 0; i--, U += (uint32_t)UN * (uint32_t)S) {
 #pragma unroll
-        for (int k = 0; k < UN; k++) vote_at(a0, U + (uint32_t)k * (uint32_t)S);
+        for (int k = 0; k + 1 < UN; k += 2) vote_at2(a0, U + (uint32_t)k * (uint32_t)S, U + (uint32_t)(k + 1) * (uint32_t)S, W0, W1);
+        if (UN & 1) vote_at(a0, U + (uint32_t)(UN - 1) * (uint32_t)S);
     }
-    for (; t <= t_hi; t++, U += (uint32_t)S) vote_at(a0, U);
+    for (int i = nvotes % UN; i > 0; i--, U += (uint32_t)S) vote_at(a0, U);
     if (t_lo <= 0 && t_hi >= 0) atomicAdd(s_acc + (y - cy0) * AP + (x - cx0), -1);
 }
 
 __global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks(const uint2 *__restrict__ edges, size_t estride,
                                                              const int2 *__restrict__ dir, int nbx, int nby, const Dims dims,
-                                                             int n_images, int32_t *cand, int32_t *ncand, int cand_cap)
+                                                             int n_images, int32_t *cand, int32_t *ncand, int cand_cap, const uint2 vw)
 {
+    // vw: the byte weights (1, pitch) of the address dot products for the first / second vote of a pair.  A kernel
+    // parameter so that they are constant-bank operands of the instruction, not immediates rebuilt inside the loop.
     extern __shared__ __align__(16) unsigned char s_raw[];
     int *s_acc = reinterpret_cast<int *>(s_raw);                       // AS x AP
     __shared__ int s_boff[VB * VB], s_bend[VB * VB + 1];               // bucket slice start / running item end
@@ -271,7 +287,7 @@ __global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks(const uint2 *__rest
             const uint2 e = __ldg(elist + s_boff[b] + (it - s_bend[b]));
             const int x = e.x & 0xffff, y = e.x >> 16;
             if (e.y == 0 || x < rx0 || x > rx1 || y < ry0 || y > ry1) continue;
-            vote_item(s_acc, s_base, e, cx0, cy0, X0, X1, Y0, Y1);
+            vote_item(s_acc, s_base, e, cx0, cy0, X0, X1, Y0, Y1, vw.x, vw.y);
         }
     }
     __syncthreads();
@@ -819,7 +835,8 @@ int hough_circles_maps(const MapSet &ms, const Dims &dims, float *mcirc, int32_t
         ScopedSection sec(SEC_VOTE, st);
         I2S_CUDA(cudaFuncSetAttribute(k_vote_peaks, cudaFuncAttributeMaxDynamicSharedMemorySize, VOTE_SMEM));
         k_vote_peaks<<<dim3(cdiv(w, AT), cdiv(h, AT), maps), VOTE_THREADS, VOTE_SMEM, st>>>(edges, plane, dir, nbx, nby, dims, ms.n,
-                                                                                           cand, ncand, lim.cand_cap);
+                                                                                           cand, ncand, lim.cand_cap,
+                                                                                           make_uint2(1u | ((uint32_t)AP << 8), (1u | ((uint32_t)AP << 8)) << 16));
         I2S_CHECK_LAUNCH("k_vote_peaks");
     }
     {

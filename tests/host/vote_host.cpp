@@ -83,6 +83,15 @@ extern "C" int vh_vote_peaks(const uint8_t *img, const uint8_t *edges, int h, in
                         const uint32_t a0 = 4u * (uint32_t)((y - cy0 - 32) * AP + (x - cx0 - 32));
                         const uint32_t addr = a0 + (m & 0xffffu) * 1u + (m >> 16) * (uint32_t)AP;
                         if (addr != 4u * (uint32_t)(ly * AP + lx)) return -2;
+                        // the paired form (vote_at2): high bytes of the halves of U(t) and U(t + 1) in one word,
+                        // fraction bits cleared, 4-way byte dot products with (1, AP, 0, 0) / (0, 0, 1, AP)
+                        const uint32_t V = U + S;
+                        const uint32_t pm = (((U >> 8) & 0xffu) | (((U >> 24) & 0xffu) << 8) | (((V >> 8) & 0xffu) << 16) |
+                                             (((V >> 24) & 0xffu) << 24)) & 0xFCFCFCFCu;
+                        const uint32_t pa0 = a0 + (pm & 0xffu) + ((pm >> 8) & 0xffu) * (uint32_t)AP;
+                        const uint32_t pa1 = a0 + ((pm >> 16) & 0xffu) + (pm >> 24) * (uint32_t)AP;
+                        if (pa0 != addr) return -2;
+                        if (t < t_hi && pa1 != 4u * (uint32_t)(((y1 + sy) >> 10) * AP + ((x1 + sx) >> 10))) return -2;
                     }
                     acc[ly * AP + lx]++;
                     cast++;
