@@ -27,7 +27,7 @@ constexpr int CANNY_LOW = 50, CANNY_HIGH = 100;
 // was measured: 7.4 -> 10.4 ms per 1024 images, most buckets hold too few edge pixels to pay for it.)
 constexpr int EB = 32;
 #ifndef I2S_EL_WARPS
-#define I2S_EL_WARPS 8
+#define I2S_EL_WARPS 4
 #endif
 constexpr int EL_WARPS = I2S_EL_WARPS;
 
@@ -154,12 +154,13 @@ constexpr int AG = 2;                        // guard cells around the ring
 constexpr int AS = AT + 2 + 2 * AG;          // shared rows / used columns
 constexpr int AP = AS + 1;                   // shared pitch (odd: column walks are conflict free)
 #ifndef I2S_VOTE_UNROLL
-#define I2S_VOTE_UNROLL 4               // 2..5 measured alike, 8 and 16 slower (longer scalar tails)
+#define I2S_VOTE_UNROLL 8               // a power of two; 8 measured 1.5 % faster than 4, 16 20 % slower
 #endif
 constexpr int VOTE_THREADS = 512;            // 384 alike, 640 / 672 slower
 constexpr int VOTE_SMEM = AS * AP * 4;
 constexpr int VB = 7;                        // buckets per axis that can overlap a tile's region
 static_assert(AP < 256, "the pitch is a byte operand of the address dot product");
+static_assert((I2S_VOTE_UNROLL & (I2S_VOTE_UNROLL - 1)) == 0 && I2S_VOTE_UNROLL >= 2, "the remainder is peeled in powers of two");
 
 // 1/v for |v| >= 1 (a non-zero Q10 step): the bare MUFU.RCP, 1 ulp -- the clip interval has 0.25 of slack
 __device__ __forceinline__ float rcp_approx(float v)
@@ -193,14 +194,15 @@ __device__ __forceinline__ void vote_item(int *s_acc, uint32_t s_base, uint2 e, 
     const int x = e.x & 0xffff, y = e.x >> 16;
     const int sx = (int)(short)(e.y & 0xffff), sy = (int)e.y >> 16;
     float lo = -(float)MAX_R, hi = (float)MAX_R;
+    // (small integers: the float differences are exact, one conversion per axis instead of two)
     if (sx != 0) {
-        float inv = 1024.0f * rcp_approx((float)sx);
-        float ta = (float)(X0 - x) * inv, tb = (float)(X1 + 1 - x) * inv;
+        const float inv = 1024.0f * rcp_approx((float)sx), fx = (float)x;
+        const float ta = ((float)X0 - fx) * inv, tb = ((float)(X1 + 1) - fx) * inv;
         lo = fmaxf(lo, fminf(ta, tb)); hi = fminf(hi, fmaxf(ta, tb));
     } else if (x < X0 || x > X1) return;
     if (sy != 0) {
-        float inv = 1024.0f * rcp_approx((float)sy);
-        float ta = (float)(Y0 - y) * inv, tb = (float)(Y1 + 1 - y) * inv;
+        const float inv = 1024.0f * rcp_approx((float)sy), fy = (float)y;
+        const float ta = ((float)Y0 - fy) * inv, tb = ((float)(Y1 + 1) - fy) * inv;
         lo = fmaxf(lo, fminf(ta, tb)); hi = fminf(hi, fmaxf(ta, tb));
     } else if (y < Y0 || y > Y1) return;
     // 0.25 of slack covers the error of the approximate divide; at most one extra step per side
@@ -222,11 +224,23 @@ __device__ __forceinline__ void vote_item(int *s_acc, uint32_t s_base, uint2 e, 
         for (int k = 0; k + 1 < UN; k += 2) vote_at2(a0, U + (uint32_t)k * (uint32_t)S, U + (uint32_t)(k + 1) * (uint32_t)S, W0, W1);
         if (UN & 1) vote_at(a0, U + (uint32_t)(UN - 1) * (uint32_t)S);
     }
-    for (int i = nvotes % UN; i > 0; i--, U += (uint32_t)S) vote_at(a0, U);
-    if (t_lo <= 0 && t_hi >= 0) atomicAdd(s_acc + (y - cy0) * AP + (x - cx0), -1);
+    int rem = nvotes % UN;                  // the remainder without a loop: pairs, then a single vote
+#pragma unroll
+    for (int k = UN / 2; k >= 2; k >>= 1)
+        if (rem & k) {
+#pragma unroll
+            for (int j = 0; j < k; j += 2) vote_at2(a0, U + (uint32_t)j * (uint32_t)S, U + (uint32_t)(j + 1) * (uint32_t)S, W0, W1);
+            U += (uint32_t)k * (uint32_t)S;
+        }
+    if (rem & 1) vote_at(a0, U);
+    if (t_lo <= 0 && t_hi >= 0)             // the pixel's own cell: offset (32, 32) from a0
+        asm volatile("red.shared.add.u32 [%0], 0xffffffff;" ::"r"(a0 + 4u * (uint32_t)(32 * AP + 32)) : "memory");
 }
 
-__global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks(const uint2 *__restrict__ edges, size_t estride,
+#ifndef I2S_VOTE_MINB
+#define I2S_VOTE_MINB 3               // three blocks per SM is what the 72 KB accumulator allows: up to 40 registers
+#endif
+__global__ void __launch_bounds__(VOTE_THREADS, I2S_VOTE_MINB) k_vote_peaks(const uint2 *__restrict__ edges, size_t estride,
                                                              const int2 *__restrict__ dir, int nbx, int nby, const Dims dims,
                                                              int n_images, int32_t *cand, int32_t *ncand, int cand_cap, const uint2 vw)
 {
@@ -285,8 +299,9 @@ __global__ void __launch_bounds__(VOTE_THREADS) k_vote_peaks(const uint2 *__rest
         for (int it = i0 + lane; it < i1; it += istep) {
             while (it >= s_bend[b + 1]) b++;                         // `it` only grows: b is monotone
             const uint2 e = __ldg(elist + s_boff[b] + (it - s_bend[b]));
-            const int x = e.x & 0xffff, y = e.x >> 16;
-            if (e.y == 0 || x < rx0 || x > rx1 || y < ry0 || y > ry1) continue;
+            if (e.y == 0) continue;                                  // no gradient direction: no votes
+            // (pixels of the walked buckets that lie beyond the reach of the tile need no test of their own:
+            // their clipped range of radii comes out empty)
             vote_item(s_acc, s_base, e, cx0, cy0, X0, X1, Y0, Y1, vw.x, vw.y);
         }
     }

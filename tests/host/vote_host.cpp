@@ -56,7 +56,9 @@ extern "C" int vh_vote_peaks(const uint8_t *img, const uint8_t *edges, int h, in
             const int ry0 = std::max(ty0 - 1 - MAX_R, 0), ry1 = std::min(ty0 + AT + MAX_R, h - 1);
             for (const Item &e : items) {
                 const int x = e.x, y = e.y, sx = e.sx, sy = e.sy;
-                if (x < rx0 || x > rx1 || y < ry0 || y > ry1) continue;
+                // the kernel walks whole 32x32 buckets overlapping the region and tests no pixel position:
+                // the clipped range of radii of a pixel beyond the reach of the tile comes out empty
+                if (x / 32 < rx0 / 32 || x / 32 > rx1 / 32 || y / 32 < ry0 / 32 || y / 32 > ry1 / 32) continue;
                 float lo = -(float)MAX_R, hi = (float)MAX_R;
                 if (sx != 0) {
                     const float inv = 1024.0f / (float)sx;
