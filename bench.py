@@ -46,7 +46,7 @@ if ROOT not in sys.path:
 
 WORKLOADS = {
     # name: (synth config, per-GPU batch, chunk)
-    "synth1024": ("synth1024", 1024, 32),
+    "synth1024": ("synth1024", 1024, 64),
     "synth2048": ("synth2048", 512, 16),
 }
 METRIC = "diagram images/sec"
