@@ -7,5 +7,5 @@ for impl in ours reference; do
      bench.py --gpus 2 --steps 10 --warmup 3 --impl $impl > gpurun_out/r2_n2_$impl.out 2> gpurun_out/r2_n2_$impl.err
   echo "$impl rc $?"; tail -1 gpurun_out/r2_n2_$impl.out | cut -c1-240
 done
-/usr/bin/time -v -o gpurun_out/r2_n1_default_time.txt timeout 900 python bench.py > gpurun_out/r2_n1_default.json 2> gpurun_out/r2_n1_default.err
-echo "default N=1 rc $?"; grep "Elapsed (wall clock)\|Maximum resident" gpurun_out/r2_n1_default_time.txt
+S=$(date +%s); timeout 900 python bench.py > gpurun_out/r2_n1_default.json 2> gpurun_out/r2_n1_default.err
+echo "default N=1 rc $? wall $(( $(date +%s) - S )) s"
