@@ -50,6 +50,17 @@ def test_bad_arguments_fail_loudly(built):
         N.check(rc, "i2s_grey")
     lim = N.default_limits()
     assert N.lib().i2s_pipeline_workspace_bytes(4, 512, 512, C.byref(lim)) > 4 * 512 * 512 * 40
+    # the masking kernel keeps 1 + circle index in 16 bits: a larger capacity is refused, not truncated
+    buf = (C.c_uint8 * 64)()
+    fl = (C.c_float * 16)()
+    cnt = (C.c_int32 * 1)(0)
+    rc = N.lib().i2s_mask_circles(buf, buf, 0, 1, 8, 8, fl, cnt, 65535, None)
+    assert rc == -1 and b"bad argument" in N.lib().i2s_last_error()
+    lim.circle_cap = 70000
+    ws = (C.c_uint8 * 64)()
+    st = (C.c_int32 * 1)()
+    rc = N.lib().i2s_hough_circles(buf, 0, 1, 8, 8, fl, cnt, st, C.byref(lim), ws, 64, None)
+    assert rc == -1
 
 
 def test_no_cpu_fallback_without_gpu():
