@@ -112,11 +112,12 @@ __global__ void __launch_bounds__(EL_WARPS * 32, 2048 / (EL_WARPS * 32)) k_edge_
         if (al4 && px >= 1 && px + 1 < w) {
             // interior pixel of a 4-byte aligned plane: the three columns of a row come out of the (at most
             // two) aligned words that hold them with one funnel shift, and the Sobel sums are byte dot
-            // products with signed weights -- six word loads and five IDP.4A instead of eight byte loads
+            // products with signed weights -- three to six word loads and five IDP.4A instead of eight byte loads
             const uint32_t a = (uint32_t)(px - 1) & ~3u, b = (uint32_t)(px + 1) & ~3u, sh = 8u * ((uint32_t)(px - 1) & 3u);
-            const uint32_t r0 = __funnelshift_r(ldg_u32(img + o0 + a), ldg_u32(img + o0 + b), sh);
-            const uint32_t r1 = __funnelshift_r(ldg_u32(img + o1 + a), ldg_u32(img + o1 + b), sh);
-            const uint32_t r2 = __funnelshift_r(ldg_u32(img + o2 + a), ldg_u32(img + o2 + b), sh);
+            const bool two = sh >= 16u;                        // the three columns straddle two words
+            const uint32_t r0 = __funnelshift_r(ldg_u32(img + o0 + a), two ? ldg_u32(img + o0 + b) : 0u, sh);
+            const uint32_t r1 = __funnelshift_r(ldg_u32(img + o1 + a), two ? ldg_u32(img + o1 + b) : 0u, sh);
+            const uint32_t r2 = __funnelshift_r(ldg_u32(img + o2 + a), two ? ldg_u32(img + o2 + b) : 0u, sh);
             dx = dp4a_us(r0, 0x000100FFu, dp4a_us(r1, 0x000200FEu, dp4a_us(r2, 0x000100FFu, 0)));   // (-1, 0, 1), (-2, 0, 2)
             dy = dp4a_us(r2, 0x00010201u, dp4a_us(r0, 0x00FFFEFFu, 0));                             // (1, 2, 1), -(1, 2, 1)
         } else {
