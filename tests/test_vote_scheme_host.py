@@ -84,3 +84,77 @@ def test_saturated_window_shortcut_is_exact(b):
             dominated = (win == value).sum(axis=(2, 3)) >= km
             assert dominated.any()
             assert (med[dominated] == value).all()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Arithmetic identities two other kernels of the circle detector rely on, restated with numpy.
+
+def test_edge_gradient_from_aligned_words():
+    """k_edge_list (circles.cu): for an interior pixel the three columns of a row come out of the one or two
+    aligned 32-bit words that hold them by a funnel shift, and the Sobel sums are byte dot products with the
+    signed weights (-1,0,1), (-2,0,2), (1,2,1), -(1,2,1): equal to the plain 3x3 Sobel for every alignment."""
+    rng = np.random.default_rng(5)
+    w = 64
+    rows = rng.integers(0, 256, (3, w), dtype=np.uint8)
+    words = rows.view("<u4")                                            # aligned words of each row
+
+    def s8(b):
+        return b - 256 if b >= 128 else b
+
+    def dp4a_us(a, wts, c):
+        return c + sum(((a >> (8 * i)) & 0xff) * s8((wts >> (8 * i)) & 0xff) for i in range(4))
+
+    for px in range(1, w - 1):
+        a, b, sh = ((px - 1) & ~3) // 4, ((px + 1) & ~3) // 4, 8 * ((px - 1) & 3)
+        r = []
+        for k in range(3):
+            lo = int(words[k, a]); hi = int(words[k, b]) if sh >= 16 else 0   # second word only when straddling
+            r.append(((hi << 32 | lo) >> sh) & 0xffffffff)
+        dx = dp4a_us(r[0], 0x000100FF, dp4a_us(r[1], 0x000200FE, dp4a_us(r[2], 0x000100FF, 0)))
+        dy = dp4a_us(r[2], 0x00010201, dp4a_us(r[0], 0x00FFFEFF, 0))
+        p = rows.astype(np.int64)
+        want_dx = (p[0, px + 1] + 2 * p[1, px + 1] + p[2, px + 1]) - (p[0, px - 1] + 2 * p[1, px - 1] + p[2, px - 1])
+        want_dy = (p[2, px - 1] + 2 * p[2, px] + p[2, px + 1]) - (p[0, px - 1] + 2 * p[0, px] + p[0, px + 1])
+        assert (dx, dy) == (want_dx, want_dy), px
+
+
+def test_radius_scan_on_packed_prefix():
+    """k_radius: the histogram is overwritten in place by (inclusive prefix sum << 16) | (1 + highest non-empty
+    bin at or below); OpenCV's scan from the top bin (every non-zero bin opens a 10-bin window, the bin just
+    below the window is skipped -- oracle/img2sgf_oracle.c, radius estimation) then needs three words per
+    window.  Same windows and counts as the plain scan, on random histograms."""
+    rng = np.random.default_rng(9)
+    NB = 290
+    for trial in range(200):
+        bins = np.zeros(NB, np.int64)
+        k = rng.integers(0, 60)
+        bins[rng.integers(0, NB, k)] += rng.integers(1, 40, k)
+        # plain scan (the oracle's loop)
+        want, j = [], NB - 1
+        while j > 0:
+            if bins[j]:
+                up, cur = j, 0
+                while j > up - 10 and j >= 0:
+                    cur += bins[j]; j -= 1
+                want.append((up, j, int(cur)))
+            j -= 1
+        # packed form
+        pref = np.cumsum(bins)
+        below, P = 0, np.zeros(NB, np.int64)
+        for b in range(NB):
+            if bins[b]:
+                below = b + 1
+            P[b] = (pref[b] << 16) | below
+        got, j = [], NB - 1
+        while j > 0:
+            up = int(P[j] & 0xffff) - 1
+            if up <= 0:
+                break
+            jn, cur = up - 10, int(P[up] >> 16)
+            if jn >= 0:
+                cur -= int(P[jn] >> 16)
+            else:
+                jn = -1
+            got.append((up, jn, cur))
+            j = jn - 1
+        assert got == want, trial
