@@ -23,6 +23,8 @@ import ctypes as C
 from dataclasses import dataclass
 from enum import Enum
 
+import zlib
+
 import numpy as np
 import torch
 
@@ -252,9 +254,21 @@ def find_circles(grey: np.ndarray, edges: np.ndarray):
     return _retrying(run)
 
 
+_lines_memo = None      # (key, result) of the last _find_lines_both call
+
+
 def _find_lines_both(masked: np.ndarray, threshold: int):
+    """Both directions come out of one pass over the image.  The reference asks for them one at a time
+    (find_lines(t, H) then find_lines(t, V), img2sgf.py:259-261): the last result is kept, keyed on the
+    image's bytes, so the second call of such a pair costs a checksum instead of a second pass."""
+    global _lines_memo
     _require_cuda()
+    masked = np.ascontiguousarray(masked, np.uint8)
     h, w = masked.shape
+    key = (h, w, int(threshold), zlib.crc32(masked), zlib.adler32(masked))
+    memo = _lines_memo
+    if memo is not None and memo[0] == key:
+        return memo[1][0].copy(), memo[1][1].copy()
     d = _dev(masked, np.uint8)
 
     def run(lim):
@@ -269,7 +283,9 @@ def _find_lines_both(masked: np.ndarray, threshold: int):
         r = rho.cpu().numpy()
         return (r[0, :c[0]].copy(), r[1, :c[1]].copy()), int(status.item())
 
-    return _retrying(run)
+    res = _retrying(run)
+    _lines_memo = (key, res)
+    return res[0].copy(), res[1].copy()
 
 
 def find_lines(masked: np.ndarray, threshold: int, direction):

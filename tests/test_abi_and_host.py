@@ -195,3 +195,30 @@ def test_gather_records_gloo_world2(tmp_path, total):
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0, out
         assert "ok" in out
+
+
+def test_find_lines_pair_runs_one_pass(monkeypatch):
+    """find_lines(t, H) followed by find_lines(t, V) on the same image (img2sgf.py:259-261) costs one pass:
+    host logic only, the device call is stubbed."""
+    from img2sgf_b200 import api
+    calls = []
+
+    def fake_retrying(fn, lim=None):
+        calls.append(1)
+        return np.array([10.0, 20.0], np.float32), np.array([5.0], np.float32)
+
+    monkeypatch.setattr(api, "_require_cuda", lambda: None)
+    monkeypatch.setattr(api, "_dev", lambda a, dt=None: a)
+    monkeypatch.setattr(api, "_retrying", fake_retrying)
+    monkeypatch.setattr(api, "_lines_memo", None)
+    img = np.zeros((32, 48), np.uint8)
+    img[5, :] = 255
+    h = api.find_lines(img, 40, api.Direction.H)
+    v = api.find_lines(img, 40, api.Direction.V)
+    assert len(calls) == 1 and h.shape == (2, 1) and v.shape == (1, 1)
+    h[0, 0] = -1.0                                             # callers own what they get
+    assert api.find_lines(img, 40, api.Direction.H)[0, 0] == 10.0 and len(calls) == 1
+    api.find_lines(img, 41, api.Direction.H)                   # another threshold: a new pass
+    img2 = img.copy(); img2[6, 3] = 255
+    api.find_lines(img2, 41, api.Direction.H)                  # another image: a new pass
+    assert len(calls) == 3
