@@ -9,7 +9,8 @@ Workload (BASELINE.json configs[3]): synthetic 1024x1024 diagrams (s=50, r=24, l
 pinned to 150), 1024 images per GPU (8192 over 8 GPUs), the whole path
 RGB array -> 19x19 board record, weak scaling over image shards with one NCCL all-gather of
 the 384-byte records.  A "step" is one pass of the path over the rank's whole batch, in chunks
-of 32 images alternating between 8 CUDA streams.
+of 64 images alternating between 8 CUDA streams.  `gpu_launches` counts this library's kernel launches in
+the whole timed region (all K steps).
 
 `value`  : images/s with the inputs already resident in HBM (CUDA events, max over ranks).
 `e2e`    : the same through the package's host-buffer call, img2sgf_b200.batch.BatchRunner.run_host():
