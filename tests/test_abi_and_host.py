@@ -222,3 +222,13 @@ def test_find_lines_pair_runs_one_pass(monkeypatch):
     img2 = img.copy(); img2[6, 3] = 255
     api.find_lines(img2, 41, api.Direction.H)                  # another image: a new pass
     assert len(calls) == 3
+
+
+def test_failed_images_flags_overflows():
+    from img2sgf_b200 import batch as B, _native as N
+    rec = np.zeros(6, N.RECORD_DTYPE)
+    rec["status"][1] = 1          # I2S_ST_CAND_OVERFLOW
+    rec["status"][3] = 8          # I2S_ST_HYST_NOT_CONVERGED
+    rec["status"][4] = N.ST_GRID_OVERFLOW
+    assert list(B.failed_images(rec)) == [1, 3, 4]
+    assert B.RETRY_BITS & N.ST_GRID_OVERFLOW == 0          # a larger limit cannot help a grid that does not fit
